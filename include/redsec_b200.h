@@ -1,0 +1,121 @@
+/*
+ * include/redsec_b200.h -- C-ABI of the B200-native TFHE bootstrap engine behind REDsec's lib/ API.
+ *
+ * This is the drop-in boundary ("B-inner"): the entry points a REDsec maintainer binds
+ * instead of lib/GPU/gates.cu + -lredcufhe.  Plain C, opaque handle, raw pointers and sizes; no torch
+ * or C++ types.  Every call is stream-ordered on the context's stream; return value 0 = RS_OK,
+ * otherwise rs_last_error() describes the failure.  There is no CPU fallback: without a CUDA device
+ * rs_ctx_create fails.
+ *
+ * Ciphertext formats
+ *   wire / host  : LWE sample = uint32[351]  (a[0..349], b)  -- TFHE LweSample order, torus32
+ *   device       : rows of RS_LWE_STRIDE=352 words (word 351 = 0) so rows are 16-byte aligned
+ * Keys (host, torus32):
+ *   bsk[n][2l][2][N]      TGSW(s_i) rows: row r = c*l + p (c = input poly, p = level), 2 output polys
+ *   ksk[N][t][base][n+1]  KS[i][j][h] = LWE(h * s'_i / base^(j+1))
+ *
+ * Each function cites the reference interface it replaces (paths relative to the REDsec tree).
+ */
+#ifndef REDSEC_B200_H
+#define REDSEC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_LWE_N 350
+#define RS_LWE_WORDS 351
+#define RS_LWE_STRIDE 352
+#define RS_TLWE_N 1024
+#define RS_BK_L 10
+#define RS_BK_BGBIT 3
+#define RS_KS_T 9
+#define RS_KS_BASEBIT 3
+#define RS_BSK_WORDS ((size_t)RS_LWE_N * 2 * RS_BK_L * 2 * RS_TLWE_N)
+#define RS_KSK_WORDS ((size_t)RS_TLWE_N * RS_KS_T * 8 * RS_LWE_WORDS)
+#define RS_EXT_STRIDE 1028
+
+enum { RS_OK = 0, RS_ERR_CUDA = 1, RS_ERR_ARG = 2, RS_ERR_STATE = 3 };
+/* gate ids: lib/GPU/gates.cu:246-286 (bootsNAND/OR/AND/NOR/XOR/XNOR) */
+enum { RS_GATE_NAND = 0, RS_GATE_OR = 1, RS_GATE_AND = 2, RS_GATE_NOR = 3, RS_GATE_XOR = 4, RS_GATE_XNOR = 5 };
+/* kernel kinds for rs_profile_get */
+enum { RS_K_BLIND_ROTATE = 0, RS_K_KEYSWITCH = 1, RS_K_LINEAR = 2, RS_K_OTHER = 3, RS_K_COUNT = 4 };
+
+typedef struct rs_ctx rs_ctx;
+
+/* -- context ------------------------------------------------------------------------------------------
+ * replaces redcufhe::SetGPUNum/Initialize(PubKey&) per device (nets/mnist/sign1024x1/net.cu:43-49),
+ * redcufhe::CleanUp() (main.cu:84), Synchronize()/CuCheckError() (main.cu:74-75). */
+int rs_ctx_create(rs_ctx **out, int device);
+int rs_ctx_destroy(rs_ctx *ctx);
+const char *rs_last_error(const rs_ctx *ctx);       /* ctx may be NULL: last creation error */
+int rs_set_stream(rs_ctx *ctx, void *cuda_stream);  /* adopt a caller-owned cudaStream_t (NULL = own stream) */
+int rs_sync(rs_ctx *ctx);
+
+/* -- evaluation key: north-star item (c) -------------------------------------------------------------
+ * replaces new_tfheGateBootstrappingCloudKeySet_fromFile -> bk->bkFFT (nets/mnist/sign1024x1/net.cpp:53-55)
+ * and ReadPubKeyFromFile + Initialize (net.cu:43-49).  Converts the BSK to the device-resident FP64
+ * Fourier layout with a CUDA kernel and the KSK to the padded device table. */
+int rs_load_eval_key(rs_ctx *ctx, const uint32_t *bsk_host, const uint32_t *ksk_host);
+
+/* -- device LWE arrays: replaces tBit/tMultiBit arrays + CtxtCopyH2D/D2H (lib/GPU/gates.cu:9-23),
+ * bit_calloc/mbit_calloc (lib/GPU/Layer.cu) */
+int rs_lwe_alloc(rs_ctx *ctx, size_t count, uint32_t **dev_out);
+int rs_lwe_free(rs_ctx *ctx, uint32_t *dev);
+int rs_lwe_upload(rs_ctx *ctx, uint32_t *dev, const uint32_t *host_wire, size_t count);
+int rs_lwe_download(rs_ctx *ctx, uint32_t *host_wire, const uint32_t *dev, size_t count);
+int rs_host_alloc(void **out, size_t bytes);        /* pinned host memory for the *_host entry points */
+int rs_host_free(void *p);
+
+/* -- the hot path ------------------------------------------------------------------------------------
+ * rs_pbs_batch: count independent programmable bootstraps in one launch,
+ *   out[c] = LWE(+mu if phase(in[c]) in [0,1/2) else -mu)
+ * replaces BinOps::binarize_int / unbinarize_int -> tfhe_bootstrap_FFT (lib/BinOps_enc.cpp:182-192) and
+ * redsec_binarize_bootstrap / redsec_unbinarize_bootstrap (lib/GPU/gates.cu:124-144), one call per layer
+ * instead of one per neuron.  in == out is allowed. */
+int rs_pbs_batch(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *in_dev, size_t count, uint32_t mu);
+/* rs_gate_batch: out[c] = boot((0,fix) +/- in0[c] +/- in1[c], mu); replaces bootsNAND..bootsXNOR
+ * (lib/GPU/gates.cu:246-286) and BinOps::max -> bootsOR (lib/BinOps_enc.cpp:164-167). */
+int rs_gate_batch(rs_ctx *ctx, int gate, uint32_t *out_dev, const uint32_t *in0_dev, const uint32_t *in1_dev,
+                  size_t count, uint32_t mu);
+/* host-buffer variants (wire format, H2D + compute + D2H inside the call): the reference-facing call a
+ * per-ciphertext caller such as lib/GPU/BinFunc_gpu.cu:599-621 would make once per layer. */
+int rs_pbs_batch_host(rs_ctx *ctx, uint32_t *out_host, const uint32_t *in_host, size_t count, uint32_t mu);
+int rs_gate_batch_host(rs_ctx *ctx, int gate, uint32_t *out_host, const uint32_t *in0_host, const uint32_t *in1_host,
+                       size_t count, uint32_t mu);
+
+/* the two halves of rs_pbs_batch, exposed so sample-extract and keyswitch can be checked bit-exactly
+ * on identical inputs: ext rows are uint32[RS_EXT_STRIDE] (a'[0..1023], b', pad) */
+int rs_blind_rotate_batch(rs_ctx *ctx, uint32_t *ext_dev, const uint32_t *in_dev, size_t count, uint32_t mu);
+int rs_keyswitch_batch(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *ext_dev, size_t count);
+int rs_ext_alloc(rs_ctx *ctx, size_t count, uint32_t **dev_out);
+int rs_ext_upload(rs_ctx *ctx, uint32_t *dev, const uint32_t *host /*[count][1025]*/, size_t count);
+int rs_ext_download(rs_ctx *ctx, uint32_t *host /*[count][1025]*/, const uint32_t *dev, size_t count);
+
+/* -- bootstrap-free neighbours ---------------------------------------------------
+ * out[o] = (0,bias[o]) + sum_k sign[k]*in[col[k]] over CSR row o; replaces the lweAddTo/lweSubTo loops of
+ * {Bin,Int}Func::Convolution/SumPooling::execute and Quantize::execute's bias add
+ * (lib/BinFunc.cpp:142-330,677-732,1044-1107; lib/IntFunc.cpp:152-319,643-700) and AddOp/SubOp
+ * (lib/GPU/gates.cu:158-202).  rowptr/col/sign/bias are DEVICE pointers (uploaded once in prep). */
+int rs_lwe_lincomb(rs_ctx *ctx, uint32_t *out_dev, size_t out_count, const uint32_t *in_dev, const int32_t *rowptr_dev,
+                   const int32_t *col_dev, const int8_t *sign_dev, const uint32_t *bias_dev /* may be NULL */);
+int rs_dev_alloc(rs_ctx *ctx, size_t bytes, void **dev_out);
+int rs_dev_free(rs_ctx *ctx, void *dev);
+int rs_dev_upload(rs_ctx *ctx, void *dev, const void *host, size_t bytes);
+int rs_dev_download(rs_ctx *ctx, void *host, const void *dev, size_t bytes);
+
+/* -- measurement ------------------------------------------------------------------------------------- */
+int rs_profile_enable(rs_ctx *ctx, int on);         /* bracket every kernel launch with CUDA events on the ctx stream */
+int rs_profile_get(rs_ctx *ctx, int kind, double *total_ms, uint64_t *launches);   /* syncs; since last reset */
+int rs_profile_reset(rs_ctx *ctx);
+uint64_t rs_launch_count(const rs_ctx *ctx);        /* kernels launched by this context since creation */
+int rs_fp64_peak(rs_ctx *ctx, double *tflops);      /* dependent-free DFMA loop on all SMs: the FP64 roofline denominator */
+int rs_set_tuning(rs_ctx *ctx, int br_groups);     /* ciphertext groups per CTA in the blind-rotate kernel: 4 or 6 */
+int rs_device_info(rs_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

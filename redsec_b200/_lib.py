@@ -1,0 +1,70 @@
+"""ctypes binding of include/redsec_b200.h.  Loading fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libredsec_b200.so")
+
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+i8p = C.POINTER(C.c_int8)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/redsec_b200.h declares
+SIGNATURES = {
+    "rs_ctx_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+    "rs_ctx_destroy": (C.c_int, [vp]),
+    "rs_last_error": (C.c_char_p, [vp]),
+    "rs_set_stream": (C.c_int, [vp, vp]),
+    "rs_sync": (C.c_int, [vp]),
+    "rs_load_eval_key": (C.c_int, [vp, u32p, u32p]),
+    "rs_lwe_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "rs_lwe_free": (C.c_int, [vp, vp]),
+    "rs_lwe_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_lwe_download": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
+    "rs_host_free": (C.c_int, [vp]),
+    "rs_pbs_batch": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_uint32]),
+    "rs_gate_batch": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_uint32]),
+    "rs_pbs_batch_host": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_uint32]),
+    "rs_gate_batch_host": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_uint32]),
+    "rs_blind_rotate_batch": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_uint32]),
+    "rs_keyswitch_batch": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_ext_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "rs_ext_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_ext_download": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_lwe_lincomb": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, vp, vp]),
+    "rs_dev_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "rs_dev_free": (C.c_int, [vp, vp]),
+    "rs_dev_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_dev_download": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_profile_enable": (C.c_int, [vp, C.c_int]),
+    "rs_profile_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "rs_profile_reset": (C.c_int, [vp]),
+    "rs_launch_count": (C.c_uint64, [vp]),
+    "rs_fp64_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
+    "rs_set_tuning": (C.c_int, [vp, C.c_int]),
+    "rs_device_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree CUDA library; raises if it is missing (build with __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise RuntimeError(
+                f"{SO} is missing: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback."
+            )
+        lib = C.CDLL(SO)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

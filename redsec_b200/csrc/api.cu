@@ -1,0 +1,489 @@
+// redsec_b200/csrc/api.cu -- C-ABI (include/redsec_b200.h) over the sm_100a kernels.
+// Replaces lib/GPU/gates.cu + libredcufhe for the bootstrap hot path (SURVEY.md 8b "B-inner").
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/redsec_b200.h"
+#include "blind_rotate.cuh"
+#include "lwe_kernels.cuh"
+#include "params.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct ProfEvent {
+    cudaEvent_t start, stop;
+    int kind;
+};
+
+}  // namespace
+
+struct rs_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    // evaluation key, device resident
+    double2* bsk_f = nullptr;     // [n][BK_ROWS][2][NH]
+    uint32_t* ksk = nullptr;      // [N][t][base][LWE_STRIDE]
+    bool key_loaded = false;
+    // scratch (grow-only; no allocation on the steady-state hot path)
+    uint32_t* ext = nullptr; size_t ext_cap = 0;        // extracted samples
+    uint32_t* lin = nullptr; size_t lin_cap = 0;        // gate pre-combination
+    uint32_t* wire = nullptr; size_t wire_cap = 0;      // wire-format staging (host variants)
+    uint32_t* io0 = nullptr; uint32_t* io1 = nullptr; size_t io_cap = 0;
+    // measurement
+    bool profiling = false;
+    std::vector<ProfEvent> events;
+    std::vector<ProfEvent> pool;
+    double prof_ms[RS_K_COUNT] = {0, 0, 0, 0};
+    uint64_t prof_n[RS_K_COUNT] = {0, 0, 0, 0};
+    uint64_t launches = 0;
+    int br_groups = 6;
+};
+
+namespace {
+
+int fail(rs_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define RS_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, RS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct LaunchScope {   // brackets one kernel launch with events when profiling is on
+    rs_ctx* ctx; int kind; ProfEvent ev{}; bool on;
+    LaunchScope(rs_ctx* c, int k) : ctx(c), kind(k), on(c->profiling) {
+        ctx->launches++;
+        if (!on) return;
+        if (!ctx->pool.empty()) { ev = ctx->pool.back(); ctx->pool.pop_back(); }
+        else { cudaEventCreate(&ev.start); cudaEventCreate(&ev.stop); }
+        ev.kind = kind;
+        cudaEventRecord(ev.start, ctx->stream);
+    }
+    ~LaunchScope() {
+        if (!on) return;
+        cudaEventRecord(ev.stop, ctx->stream);
+        ctx->events.push_back(ev);
+    }
+};
+
+int grow(rs_ctx* ctx, uint32_t** p, size_t* cap, size_t words) {
+    if (*cap >= words) return RS_OK;
+    if (*p) RS_CUDA(ctx, cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    RS_CUDA(ctx, cudaMalloc(p, words * sizeof(uint32_t)));
+    *cap = words;
+    return RS_OK;
+}
+
+// Blind-rotation variants: (ciphertext groups per CTA, BSK ring stages).  4 groups = 8 warps = 2 per SM
+// sub-partition (255 registers/thread, no spills); 6 groups = 12 warps = 3 per sub-partition (168 registers).
+struct BrVariant { int groups, stages, smem; void (*set_attr)(cudaError_t*); };
+template <int G, int S>
+void br_launch(rs_ctx* ctx, int grid, const uint32_t* in, int count, uint32_t mu, uint32_t* ext) {
+    rs::blind_rotate_kernel<G, S><<<grid, G * 64, rs::BrSmem<G, S>::kTotal, ctx->stream>>>(in, count, mu, ctx->bsk_f, ext);
+}
+template <int G, int S>
+cudaError_t br_prepare() {
+    return cudaFuncSetAttribute(rs::blind_rotate_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::BrSmem<G, S>::kTotal);
+}
+constexpr int kMaxSmemNeeded = rs::BrSmem<6, 4>::kTotal;
+
+int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t count, uint32_t mu) {
+    if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
+    if (count == 0) return RS_OK;
+    const int G = ctx->br_groups;
+    const int grid = (int)((count + G - 1) / G);
+    {
+        LaunchScope ls(ctx, RS_K_BLIND_ROTATE);
+        if (G == 4) br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext);
+        else br_launch<6, 4>(ctx, grid, in, (int)count, mu, ext);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+constexpr int kKsTile = 4;
+int launch_keyswitch(rs_ctx* ctx, uint32_t* out, const uint32_t* ext, size_t count) {
+    if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
+    if (count == 0) return RS_OK;
+    const int grid = (int)((count + kKsTile - 1) / kKsTile);
+    {
+        LaunchScope ls(ctx, RS_K_KEYSWITCH);
+        rs::keyswitch_kernel<kKsTile><<<grid, rs::LWE_STRIDE, 0, ctx->stream>>>(ext, (int)count, ctx->ksk, out);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+int grid_for(rs_ctx* ctx, size_t total, int block) {
+    size_t g = (total + block - 1) / block;
+    size_t cap = (size_t)ctx->sm_count * 16;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+// DFMA throughput probe: 8 independent chains per thread
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rs_ctx_create(rs_ctx** out, int device) {
+    if (!out) return fail(nullptr, RS_ERR_ARG, "rs_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RS_ERR_CUDA, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, RS_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    RS_CUDA(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RS_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, RS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    if ((size_t)prop.sharedMemPerBlockOptin < (size_t)kMaxSmemNeeded)
+        return fail(nullptr, RS_ERR_CUDA, "device offers %zu B opt-in shared memory, kernel needs %d", (size_t)prop.sharedMemPerBlockOptin, kMaxSmemNeeded);
+    rs_ctx* ctx = new rs_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    e = br_prepare<4, 4>();
+    if (e == cudaSuccess) e = br_prepare<6, 4>();
+    if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
+    if (const char* env = getenv("RS_BR_GROUPS")) { int g = atoi(env); if (g == 4 || g == 6) ctx->br_groups = g; }
+    *out = ctx;
+    return RS_OK;
+}
+
+int rs_ctx_destroy(rs_ctx* ctx) {
+    if (!ctx) return RS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& ev : ctx->events) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
+    for (auto& ev : ctx->pool) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
+    cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->ext); cudaFree(ctx->lin); cudaFree(ctx->wire);
+    cudaFree(ctx->io0); cudaFree(ctx->io1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RS_OK;
+}
+
+const char* rs_last_error(const rs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rs_set_stream(rs_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return RS_ERR_ARG;
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (cuda_stream) {
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else if (!ctx->own_stream) {
+        RS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return RS_OK;
+}
+
+int rs_sync(rs_ctx* ctx) {
+    if (!ctx) return RS_ERR_ARG;
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_load_eval_key(rs_ctx* ctx, const uint32_t* bsk_host, const uint32_t* ksk_host) {
+    if (!ctx || !bsk_host || !ksk_host) return fail(ctx, RS_ERR_ARG, "rs_load_eval_key: NULL argument");
+    RS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->bsk_f) RS_CUDA(ctx, cudaMalloc(&ctx->bsk_f, rs::BSK_F_BYTES));
+    if (!ctx->ksk) RS_CUDA(ctx, cudaMalloc(&ctx->ksk, rs::KSK_DEV_WORDS * sizeof(uint32_t)));
+    // staging for the torus32 keys (freed after conversion)
+    uint32_t* stage = nullptr;
+    const size_t ksk_bytes = RS_KSK_WORDS * sizeof(uint32_t), bsk_bytes = RS_BSK_WORDS * sizeof(uint32_t);
+    RS_CUDA(ctx, cudaMalloc(&stage, ksk_bytes > bsk_bytes ? ksk_bytes : bsk_bytes));
+    RS_CUDA(ctx, cudaMemcpyAsync(stage, bsk_host, bsk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int npolys = rs::LWE_N * rs::BK_ROWS * 2;
+    {
+        LaunchScope ls(ctx, RS_K_OTHER);
+        rs::bsk_to_fourier_kernel<<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(reinterpret_cast<const int32_t*>(stage), ctx->bsk_f, npolys);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RS_CUDA(ctx, cudaMemcpyAsync(stage, ksk_host, ksk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t rows = (size_t)rs::N * rs::KS_T * rs::KS_BASE;
+    {
+        LaunchScope ls(ctx, RS_K_OTHER);
+        rs::ksk_pad_kernel<<<grid_for(ctx, rows * rs::LWE_STRIDE, 256), 256, 0, ctx->stream>>>(stage, ctx->ksk, rows);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RS_CUDA(ctx, cudaFree(stage));
+    ctx->key_loaded = true;
+    return RS_OK;
+}
+
+int rs_lwe_alloc(rs_ctx* ctx, size_t count, uint32_t** dev_out) {
+    if (!ctx || !dev_out) return fail(ctx, RS_ERR_ARG, "rs_lwe_alloc: NULL argument");
+    RS_CUDA(ctx, cudaSetDevice(ctx->device));
+    RS_CUDA(ctx, cudaMalloc(dev_out, (count ? count : 1) * rs::LWE_STRIDE * sizeof(uint32_t)));
+    return RS_OK;
+}
+int rs_lwe_free(rs_ctx* ctx, uint32_t* dev) {
+    if (!ctx) return RS_ERR_ARG;
+    RS_CUDA(ctx, cudaFree(dev));
+    return RS_OK;
+}
+int rs_lwe_upload(rs_ctx* ctx, uint32_t* dev, const uint32_t* host_wire, size_t count) {
+    if (!ctx || !dev || !host_wire) return fail(ctx, RS_ERR_ARG, "rs_lwe_upload: NULL argument");
+    if (count == 0) return RS_OK;
+    if (int r = grow(ctx, &ctx->wire, &ctx->wire_cap, count * rs::LWE_WORDS)) return r;
+    RS_CUDA(ctx, cudaMemcpyAsync(ctx->wire, host_wire, count * rs::LWE_WORDS * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, RS_K_OTHER);
+        rs::lwe_pad_kernel<<<grid_for(ctx, count * rs::LWE_STRIDE, 256), 256, 0, ctx->stream>>>(ctx->wire, dev, (int)count);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+int rs_lwe_download(rs_ctx* ctx, uint32_t* host_wire, const uint32_t* dev, size_t count) {
+    if (!ctx || !dev || !host_wire) return fail(ctx, RS_ERR_ARG, "rs_lwe_download: NULL argument");
+    if (count == 0) return RS_OK;
+    if (int r = grow(ctx, &ctx->wire, &ctx->wire_cap, count * rs::LWE_WORDS)) return r;
+    {
+        LaunchScope ls(ctx, RS_K_OTHER);
+        rs::lwe_unpad_kernel<<<grid_for(ctx, count * rs::LWE_WORDS, 256), 256, 0, ctx->stream>>>(dev, ctx->wire, (int)count);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    RS_CUDA(ctx, cudaMemcpyAsync(host_wire, ctx->wire, count * rs::LWE_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RS_OK;
+}
+int rs_host_alloc(void** out, size_t bytes) {
+    if (!out) return RS_ERR_ARG;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? RS_OK : RS_ERR_CUDA;
+}
+int rs_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? RS_OK : RS_ERR_CUDA; }
+
+int rs_blind_rotate_batch(rs_ctx* ctx, uint32_t* ext_dev, const uint32_t* in_dev, size_t count, uint32_t mu) {
+    if (!ctx || !ext_dev || !in_dev) return fail(ctx, RS_ERR_ARG, "rs_blind_rotate_batch: NULL argument");
+    return launch_blind_rotate(ctx, ext_dev, in_dev, count, mu);
+}
+int rs_keyswitch_batch(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* ext_dev, size_t count) {
+    if (!ctx || !ext_dev || !out_dev) return fail(ctx, RS_ERR_ARG, "rs_keyswitch_batch: NULL argument");
+    return launch_keyswitch(ctx, out_dev, ext_dev, count);
+}
+int rs_ext_alloc(rs_ctx* ctx, size_t count, uint32_t** dev_out) {
+    if (!ctx || !dev_out) return fail(ctx, RS_ERR_ARG, "rs_ext_alloc: NULL argument");
+    RS_CUDA(ctx, cudaMalloc(dev_out, (count ? count : 1) * rs::EXT_STRIDE * sizeof(uint32_t)));
+    return RS_OK;
+}
+int rs_ext_upload(rs_ctx* ctx, uint32_t* dev, const uint32_t* host, size_t count) {
+    if (!ctx || !dev || !host) return fail(ctx, RS_ERR_ARG, "rs_ext_upload: NULL argument");
+    RS_CUDA(ctx, cudaMemsetAsync(dev, 0, count * rs::EXT_STRIDE * sizeof(uint32_t), ctx->stream));
+    RS_CUDA(ctx, cudaMemcpy2DAsync(dev, rs::EXT_STRIDE * 4, host, (rs::N + 1) * 4, (rs::N + 1) * 4, count, cudaMemcpyHostToDevice, ctx->stream));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RS_OK;
+}
+int rs_ext_download(rs_ctx* ctx, uint32_t* host, const uint32_t* dev, size_t count) {
+    if (!ctx || !dev || !host) return fail(ctx, RS_ERR_ARG, "rs_ext_download: NULL argument");
+    RS_CUDA(ctx, cudaMemcpy2DAsync(host, (rs::N + 1) * 4, dev, rs::EXT_STRIDE * 4, (rs::N + 1) * 4, count, cudaMemcpyDeviceToHost, ctx->stream));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RS_OK;
+}
+
+int rs_pbs_batch(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* in_dev, size_t count, uint32_t mu) {
+    if (!ctx || !out_dev || !in_dev) return fail(ctx, RS_ERR_ARG, "rs_pbs_batch: NULL argument");
+    if (int r = grow(ctx, &ctx->ext, &ctx->ext_cap, count * rs::EXT_STRIDE)) return r;
+    if (int r = launch_blind_rotate(ctx, ctx->ext, in_dev, count, mu)) return r;
+    return launch_keyswitch(ctx, out_dev, ctx->ext, count);
+}
+
+int rs_gate_batch(rs_ctx* ctx, int gate, uint32_t* out_dev, const uint32_t* in0_dev, const uint32_t* in1_dev, size_t count,
+                  uint32_t mu) {
+    if (!ctx || !out_dev || !in0_dev || !in1_dev) return fail(ctx, RS_ERR_ARG, "rs_gate_batch: NULL argument");
+    if (gate < 0 || gate > RS_GATE_XNOR) return fail(ctx, RS_ERR_ARG, "rs_gate_batch: unknown gate %d", gate);
+    if (count == 0) return RS_OK;
+    // lib/GPU/gates.cu:246-286: NAND fix=+1/8, OR +1/8, AND -1/8, NOR -1/8, XOR +1/4 (x2), XNOR -1/4 (x2)
+    static const uint32_t fix[6] = {0x20000000u, 0x20000000u, 0xE0000000u, 0xE0000000u, 0x40000000u, 0xC0000000u};
+    static const uint32_t mul[6] = {0xFFFFFFFFu, 1u, 1u, 0xFFFFFFFFu, 2u, 0xFFFFFFFEu};
+    if (int r = grow(ctx, &ctx->lin, &ctx->lin_cap, count * rs::LWE_STRIDE)) return r;
+    {
+        LaunchScope ls(ctx, RS_K_LINEAR);
+        rs::gate_linear_kernel<<<grid_for(ctx, count * rs::LWE_STRIDE, 256), 256, 0, ctx->stream>>>(ctx->lin, in0_dev, in1_dev,
+                                                                                                 (int)count, mul[gate], fix[gate]);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return rs_pbs_batch(ctx, out_dev, ctx->lin, count, mu);
+}
+
+static int ensure_io(rs_ctx* ctx, size_t count) {
+    if (ctx->io_cap >= count) return RS_OK;
+    if (ctx->io0) cudaFree(ctx->io0);
+    if (ctx->io1) cudaFree(ctx->io1);
+    ctx->io0 = ctx->io1 = nullptr; ctx->io_cap = 0;
+    RS_CUDA(ctx, cudaMalloc(&ctx->io0, count * rs::LWE_STRIDE * sizeof(uint32_t)));
+    RS_CUDA(ctx, cudaMalloc(&ctx->io1, count * rs::LWE_STRIDE * sizeof(uint32_t)));
+    ctx->io_cap = count;
+    return RS_OK;
+}
+
+int rs_pbs_batch_host(rs_ctx* ctx, uint32_t* out_host, const uint32_t* in_host, size_t count, uint32_t mu) {
+    if (!ctx || !out_host || !in_host) return fail(ctx, RS_ERR_ARG, "rs_pbs_batch_host: NULL argument");
+    if (int r = ensure_io(ctx, count)) return r;
+    if (int r = rs_lwe_upload(ctx, ctx->io0, in_host, count)) return r;
+    if (int r = rs_pbs_batch(ctx, ctx->io0, ctx->io0, count, mu)) return r;
+    return rs_lwe_download(ctx, out_host, ctx->io0, count);
+}
+
+int rs_gate_batch_host(rs_ctx* ctx, int gate, uint32_t* out_host, const uint32_t* in0_host, const uint32_t* in1_host,
+                       size_t count, uint32_t mu) {
+    if (!ctx || !out_host || !in0_host || !in1_host) return fail(ctx, RS_ERR_ARG, "rs_gate_batch_host: NULL argument");
+    if (int r = ensure_io(ctx, count)) return r;
+    if (int r = rs_lwe_upload(ctx, ctx->io0, in0_host, count)) return r;
+    if (int r = rs_lwe_upload(ctx, ctx->io1, in1_host, count)) return r;
+    if (int r = rs_gate_batch(ctx, gate, ctx->io0, ctx->io0, ctx->io1, count, mu)) return r;
+    return rs_lwe_download(ctx, out_host, ctx->io0, count);
+}
+
+int rs_lwe_lincomb(rs_ctx* ctx, uint32_t* out_dev, size_t out_count, const uint32_t* in_dev, const int32_t* rowptr_dev,
+                   const int32_t* col_dev, const int8_t* sign_dev, const uint32_t* bias_dev) {
+    if (!ctx || !out_dev || !in_dev || !rowptr_dev) return fail(ctx, RS_ERR_ARG, "rs_lwe_lincomb: NULL argument");
+    if (out_count == 0) return RS_OK;
+    const size_t cap = (size_t)ctx->sm_count * 32;
+    const int grid = (int)(out_count < cap ? out_count : cap);
+    {
+        LaunchScope ls(ctx, RS_K_LINEAR);
+        rs::lwe_lincomb_kernel<<<grid, rs::LWE_STRIDE / 4, 0, ctx->stream>>>(out_dev, (int)out_count, in_dev, rowptr_dev, col_dev,
+                                                                            sign_dev, bias_dev);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_dev_alloc(rs_ctx* ctx, size_t bytes, void** dev_out) {
+    if (!ctx || !dev_out) return fail(ctx, RS_ERR_ARG, "rs_dev_alloc: NULL argument");
+    RS_CUDA(ctx, cudaSetDevice(ctx->device));
+    RS_CUDA(ctx, cudaMalloc(dev_out, bytes ? bytes : 1));
+    return RS_OK;
+}
+int rs_dev_free(rs_ctx* ctx, void* dev) {
+    if (!ctx) return RS_ERR_ARG;
+    RS_CUDA(ctx, cudaFree(dev));
+    return RS_OK;
+}
+int rs_dev_upload(rs_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    if (!ctx || !dev || !host) return fail(ctx, RS_ERR_ARG, "rs_dev_upload: NULL argument");
+    RS_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RS_OK;
+}
+int rs_dev_download(rs_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    if (!ctx || !dev || !host) return fail(ctx, RS_ERR_ARG, "rs_dev_download: NULL argument");
+    RS_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RS_OK;
+}
+
+int rs_profile_enable(rs_ctx* ctx, int on) {
+    if (!ctx) return RS_ERR_ARG;
+    ctx->profiling = on != 0;
+    return RS_OK;
+}
+static int profile_drain(rs_ctx* ctx) {
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& ev : ctx->events) {
+        float ms = 0.f;
+        RS_CUDA(ctx, cudaEventElapsedTime(&ms, ev.start, ev.stop));
+        ctx->prof_ms[ev.kind] += ms;
+        ctx->prof_n[ev.kind] += 1;
+        ctx->pool.push_back(ev);
+    }
+    ctx->events.clear();
+    return RS_OK;
+}
+int rs_profile_get(rs_ctx* ctx, int kind, double* total_ms, uint64_t* launches) {
+    if (!ctx || kind < 0 || kind >= RS_K_COUNT) return fail(ctx, RS_ERR_ARG, "rs_profile_get: bad argument");
+    if (int r = profile_drain(ctx)) return r;
+    if (total_ms) *total_ms = ctx->prof_ms[kind];
+    if (launches) *launches = ctx->prof_n[kind];
+    return RS_OK;
+}
+int rs_profile_reset(rs_ctx* ctx) {
+    if (!ctx) return RS_ERR_ARG;
+    if (int r = profile_drain(ctx)) return r;
+    for (int k = 0; k < RS_K_COUNT; k++) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+    return RS_OK;
+}
+uint64_t rs_launch_count(const rs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rs_fp64_peak(rs_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return fail(ctx, RS_ERR_ARG, "rs_fp64_peak: NULL argument");
+    const int block = 256, grid = ctx->sm_count * 8, iters = 20000;
+    double* out = nullptr;
+    RS_CUDA(ctx, cudaMalloc(&out, (size_t)grid * block * sizeof(double)));
+    cudaEvent_t e0, e1;
+    RS_CUDA(ctx, cudaEventCreate(&e0));
+    RS_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        RS_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        fp64_peak_kernel<<<grid, block, 0, ctx->stream>>>(out, iters);
+        ctx->launches++;
+        RS_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        RS_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = 2.0 * 8.0 * (double)iters * grid * block / (best * 1e-3) / 1e12;
+    return RS_OK;
+}
+
+int rs_set_tuning(rs_ctx* ctx, int br_groups) {
+    if (!ctx || (br_groups != 4 && br_groups != 6)) return fail(ctx, RS_ERR_ARG, "rs_set_tuning: br_groups must be 4 or 6");
+    ctx->br_groups = br_groups;
+    return RS_OK;
+}
+
+int rs_device_info(rs_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {
+    if (!ctx) return RS_ERR_ARG;
+    cudaDeviceProp prop;
+    RS_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (smem_optin) *smem_optin = prop.sharedMemPerBlockOptin;
+    return RS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""GPU parity of the bootstrap hot path against the CPU oracle, through the C-ABI.
+Bar (north star): bit-exact ciphertexts for keyswitch / sample extract / full PBS on identical inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MU8 = 0x20000000       # 1/8
+MU4096 = 0x00100000    # 1/4096
+
+
+def _rand_bits_ct(O, ks, count, mu, alpha, seed):
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, count)
+    msg = np.where(bits == 1, mu, (-mu) & 0xFFFFFFFF)
+    return bits, O.encrypt(msg, alpha, ks.lwe_key, seed)
+
+
+def test_blind_rotate_extract_bit_exact(oracle, keyset, engine):
+    O = oracle
+    bits, ct = _rand_bits_ct(O, keyset, 13, MU8, 2.0 ** -25, 11)
+    dev = engine.upload(ct)
+    ext_gpu = engine.blind_rotate(dev, MU8)
+    for c in range(ct.shape[0]):
+        acc = O.blind_rotate(ct[c], MU8, keyset, exact=(c < 2))
+        assert np.array_equal(ext_gpu[c], O.sample_extract(acc)), f"ciphertext {c}"
+
+
+def test_keyswitch_bit_exact(oracle, keyset, engine):
+    rng = np.random.default_rng(5)
+    ext = rng.integers(0, 2 ** 32, size=(9, 1025), dtype=np.uint64).astype(np.uint32)
+    got = engine.keyswitch(ext)
+    want = oracle.keyswitch(ext, keyset)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("count", [1, 5, 6, 7, 300])
+def test_pbs_bit_exact_and_decrypts(oracle, keyset, engine, count):
+    O = oracle
+    bits, ct = _rand_bits_ct(O, keyset, count, MU4096, 2.0 ** -15, 100 + count)
+    got = engine.download(engine.pbs(engine.upload(ct), MU4096))
+    want = O.pbs(ct, MU4096, keyset)
+    assert np.array_equal(got, want)
+    dec = O.decrypt(got, keyset.lwe_key, 4096)
+    assert np.array_equal(dec, np.where(bits == 1, 1, -1))
+
+
+@pytest.mark.parametrize("groups", [4, 6])
+def test_variants_agree(oracle, keyset, engine, groups):
+    bits, ct = _rand_bits_ct(oracle, keyset, 29, MU8, 2.0 ** -25, 77)
+    engine.set_tuning(groups)
+    try:
+        got = engine.download(engine.pbs(engine.upload(ct), MU8))
+    finally:
+        engine.set_tuning(6)
+    assert np.array_equal(got, oracle.pbs(ct, MU8, keyset))
+
+
+@pytest.mark.parametrize("op,fn", [("NAND", lambda a, b: 1 - (a & b)), ("OR", lambda a, b: a | b),
+                                    ("AND", lambda a, b: a & b), ("NOR", lambda a, b: 1 - (a | b)),
+                                    ("XOR", lambda a, b: a ^ b), ("XNOR", lambda a, b: 1 - (a ^ b))])
+def test_gates_bit_exact(oracle, keyset, engine, op, fn):
+    O = oracle
+    a_bits, a = _rand_bits_ct(O, keyset, 40, MU8, 2.0 ** -25, 21)
+    b_bits, b = _rand_bits_ct(O, keyset, 40, MU8, 2.0 ** -25, 22)
+    got = engine.download(engine.gate(op, engine.upload(a), engine.upload(b), MU8))
+    want = O.gate(op, a, b, MU8, keyset)
+    assert np.array_equal(got, want)
+    dec = (O.decrypt(got, keyset.lwe_key, 8) > 0).astype(int)
+    assert np.array_equal(dec, fn(a_bits, b_bits))
+
+
+def test_host_entry_points_match_device(oracle, keyset, engine):
+    bits, ct = _rand_bits_ct(oracle, keyset, 17, MU8, 2.0 ** -25, 31)
+    got = engine.pbs_host(ct, MU8)
+    assert np.array_equal(got, oracle.pbs(ct, MU8, keyset))
+    got2 = engine.gate_host("NAND", ct, ct[::-1].copy(), MU8)
+    assert np.array_equal(got2, oracle.gate("NAND", ct, ct[::-1].copy(), MU8, keyset))
