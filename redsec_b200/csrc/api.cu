@@ -48,7 +48,7 @@ struct rs_ctx {
     double prof_ms[RS_K_COUNT] = {0, 0, 0, 0};
     uint64_t prof_n[RS_K_COUNT] = {0, 0, 0, 0};
     uint64_t launches = 0;
-    int br_groups = 6;
+    int br_groups = 4;
 };
 
 namespace {

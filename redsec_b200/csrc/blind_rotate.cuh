@@ -123,7 +123,7 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
         acc[j] = 0;
         acc[N + j] = (((j + barb) & (2 * N - 1)) < N) ? mu : 0u - mu;   // X^{2N-barb} * (mu + mu X + ...)
     }
-    Twiddles tw;
+    TwiddlesT<(GROUPS > 4)> tw;
     make_twiddles(tw, t);
     group_sync(g);
 

@@ -1,0 +1,212 @@
+// redsec_b200/csrc/client.cpp -- client side of the boundary: keyset generation, LWE encryption / decryption and
+// the on-disk formats.  Host C++; product code (independent of oracle/).
+//
+// Replaces client/gen_secure_keyset.cpp:94-120 (keygen with redsec_params_small_v2, seed {0,0,0}),
+// client/encrypt_image.cpp:65-85 (lweSymEncrypt(modSwitchToTorus32(2p-255,4096), 2^-15)) and
+// client/decrypt_image.cpp:46-63 (lweSymDecrypt + modSwitchFromTorus32, centred, argmax).
+//
+// Randomness: a documented deterministic generator (splitmix64-seeded xoshiro256**, Box-Muller), see
+// DESIGN.md "Keyset"; upstream TFHE's std::default_random_engine stream is not reproduced (there is no
+// upstream fixture to compare against).  File layouts are this repo's own and are self-round-trip
+// tested; compatibility with files written by upstream TFHE is NOT claimed.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/redsec_b200.h"
+#include "params.h"
+
+namespace {
+
+class Xoshiro {
+public:
+    Xoshiro(uint64_t seed, uint64_t domain, uint64_t index) {
+        uint64_t x = seed + 0x632BE59BD9B4E019ULL * (domain + 1) + 0xD1342543DE82EF95ULL * index;
+        for (auto& w : s_) w = splitmix(x);
+    }
+    uint64_t next() {
+        const uint64_t r = rotl(s_[1] * 5, 7) * 9, t = s_[1] << 17;
+        s_[2] ^= s_[0]; s_[3] ^= s_[1]; s_[1] ^= s_[2]; s_[0] ^= s_[3]; s_[2] ^= t; s_[3] = rotl(s_[3], 45);
+        return r;
+    }
+    uint32_t word() { return static_cast<uint32_t>(next() >> 32); }
+    int32_t bit() { return static_cast<int32_t>(next() >> 63); }
+    double unit() { return static_cast<double>((next() >> 11) + 1) * 0x1.0p-53; }   // (0,1]
+    double gauss(double sigma) {
+        const double u1 = unit(), u2 = unit();
+        return sigma * std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925286766559 * u2);
+    }
+private:
+    static uint64_t rotl(uint64_t v, int k) { return (v << k) | (v >> (64 - k)); }
+    static uint64_t splitmix(uint64_t& x) {
+        uint64_t z = (x += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    uint64_t s_[4];
+};
+
+enum : uint64_t { DOM_LWE_KEY = 1, DOM_TLWE_KEY = 2, DOM_BSK = 3, DOM_KSK = 4, DOM_ENC = 5 };
+
+inline uint32_t double_to_torus32(double d) {   // TFHE dtot32
+    return static_cast<uint32_t>(static_cast<int32_t>(static_cast<int64_t>((d - static_cast<double>(static_cast<int64_t>(d))) * 4294967296.0)));
+}
+
+// b += a * s in Z[X]/(X^N+1) for a binary key s given by the positions of its ones
+void add_negacyclic_product(uint32_t* b, const uint32_t* a, const std::vector<int>& ones) {
+    using rs::N;
+    for (int m : ones) {
+        // X^m * a: coefficients j >= m take +a[j-m], coefficients j < m take -a[j-m+N]
+        for (int j = m; j < N; j++) b[j] += a[j - m];
+        for (int j = 0; j < m; j++) b[j] -= a[j - m + N];
+    }
+}
+
+struct FileCloser { void operator()(FILE* f) const { if (f) fclose(f); } };
+using File = std::unique_ptr<FILE, FileCloser>;
+
+const char kSecretMagic[8] = {'R', 'S', 'B', '2', 'S', 'K', '0', '1'};
+const char kEvalMagic[8] = {'R', 'S', 'B', '2', 'E', 'K', '0', '1'};
+const int32_t kParamBlock[8] = {rs::LWE_N, rs::N, 1, rs::BK_L, rs::BK_BGBIT, rs::KS_T, rs::KS_BASEBIT, 0};
+
+bool write_all(FILE* f, const void* p, size_t bytes) { return fwrite(p, 1, bytes, f) == bytes; }
+bool read_all(FILE* f, void* p, size_t bytes) { return fread(p, 1, bytes, f) == bytes; }
+bool check_header(FILE* f, const char (&magic)[8]) {
+    char m[8]; int32_t pb[8];
+    return read_all(f, m, 8) && read_all(f, pb, sizeof(pb)) && !memcmp(m, magic, 8) && !memcmp(pb, kParamBlock, sizeof(pb));
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t rs_modswitch_to_torus32(int32_t mu, int32_t msize) {
+    const uint64_t interv = ((UINT64_C(1) << 63) / static_cast<uint64_t>(msize)) * 2;
+    return static_cast<uint32_t>((static_cast<uint64_t>(static_cast<int64_t>(mu)) * interv) >> 32);
+}
+int32_t rs_modswitch_from_torus32(uint32_t phase, int32_t msize) {
+    const uint64_t interv = ((UINT64_C(1) << 63) / static_cast<uint64_t>(msize)) * 2;
+    return static_cast<int32_t>(((static_cast<uint64_t>(phase) << 32) + interv / 2) / interv);
+}
+
+int rs_keygen(uint64_t seed, int32_t* lwe_key, int32_t* tlwe_key, uint32_t* bsk, uint32_t* ksk) {
+    if (!lwe_key || !tlwe_key || !bsk || !ksk) return RS_ERR_ARG;
+    using namespace rs;
+    { Xoshiro g(seed, DOM_LWE_KEY, 0); for (int i = 0; i < LWE_N; i++) lwe_key[i] = g.bit(); }
+    { Xoshiro g(seed, DOM_TLWE_KEY, 0); for (int i = 0; i < N; i++) tlwe_key[i] = g.bit(); }
+    std::vector<int> ones;
+    for (int i = 0; i < N; i++) if (tlwe_key[i]) ones.push_back(i);
+    const double sigma_bk = std::ldexp(1.0, -30), sigma_ks = std::ldexp(1.0, -25);   // gen_secure_keyset.cpp:75-77
+    const int rows = LWE_N * BK_ROWS;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int row = 0; row < rows; row++) {
+        Xoshiro g(seed, DOM_BSK, static_cast<uint64_t>(row));
+        uint32_t* mask = bsk + static_cast<size_t>(row) * 2 * N;
+        uint32_t* body = mask + N;
+        for (int j = 0; j < N; j++) mask[j] = g.word();
+        for (int j = 0; j < N; j++) body[j] = double_to_torus32(g.gauss(sigma_bk));
+        add_negacyclic_product(body, mask, ones);
+        const int i = row / BK_ROWS, c = (row % BK_ROWS) / BK_L, p = row % BK_L;
+        const uint32_t gadget = static_cast<uint32_t>(lwe_key[i]) << (32 - (p + 1) * BK_BGBIT);   // s_i * Bg^-(p+1)
+        (c ? body : mask)[0] += gadget;
+    }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int i = 0; i < N; i++) {
+        Xoshiro g(seed, DOM_KSK, static_cast<uint64_t>(i));
+        for (int j = 0; j < KS_T; j++)
+            for (int h = 0; h < KS_BASE; h++) {
+                uint32_t* ct = ksk + ((static_cast<size_t>(i) * KS_T + j) * KS_BASE + h) * LWE_WORDS;
+                uint32_t dot = 0;
+                for (int x = 0; x < LWE_N; x++) { ct[x] = g.word(); dot += lwe_key[x] ? ct[x] : 0u; }
+                const uint32_t msg = static_cast<uint32_t>(h * tlwe_key[i]) << (32 - (j + 1) * KS_BASEBIT);
+                ct[LWE_N] = dot + double_to_torus32(g.gauss(sigma_ks)) + msg;
+            }
+    }
+    return RS_OK;
+}
+
+int rs_lwe_encrypt(uint32_t* ct, const uint32_t* mu, size_t count, double alpha, const int32_t* lwe_key, uint64_t seed) {
+    if (!ct || !mu || !lwe_key) return RS_ERR_ARG;
+    using namespace rs;
+#pragma omp parallel for schedule(static)
+    for (long c = 0; c < static_cast<long>(count); c++) {
+        Xoshiro g(seed, DOM_ENC, static_cast<uint64_t>(c));
+        uint32_t* s = ct + static_cast<size_t>(c) * LWE_WORDS;
+        uint32_t dot = 0;
+        for (int x = 0; x < LWE_N; x++) { s[x] = g.word(); dot += lwe_key[x] ? s[x] : 0u; }
+        s[LWE_N] = dot + double_to_torus32(g.gauss(alpha)) + mu[c];
+    }
+    return RS_OK;
+}
+
+int rs_lwe_phase(uint32_t* phase, const uint32_t* ct, size_t count, const int32_t* lwe_key) {
+    if (!phase || !ct || !lwe_key) return RS_ERR_ARG;
+    using namespace rs;
+    for (size_t c = 0; c < count; c++) {
+        const uint32_t* s = ct + c * LWE_WORDS;
+        uint32_t dot = 0;
+        for (int x = 0; x < LWE_N; x++) dot += lwe_key[x] ? s[x] : 0u;
+        phase[c] = s[LWE_N] - dot;
+    }
+    return RS_OK;
+}
+
+// client/decrypt_image.cpp:52-58: modSwitchFromTorus32(lweSymDecrypt(ct, key, msize), msize), centred
+int rs_lwe_decrypt(int32_t* msg, const uint32_t* ct, size_t count, const int32_t* lwe_key, int32_t msize) {
+    if (!msg || msize <= 0) return RS_ERR_ARG;
+    std::vector<uint32_t> ph(count);
+    if (int r = rs_lwe_phase(ph.data(), ct, count, lwe_key)) return r;
+    for (size_t c = 0; c < count; c++) {
+        int32_t v = rs_modswitch_from_torus32(ph[c], msize) % msize;
+        msg[c] = v > msize / 2 ? v - msize : v;
+    }
+    return RS_OK;
+}
+
+// ---- files.  secret.key / eval.key: magic[8], int32 params[8], payload.  *.ctxt: per sample n x int32 a, int32 b,
+// double variance (the content order recalled for TFHE's export_lweSample), no header.
+int rs_write_secret_key(const char* path, const int32_t* lwe_key, const int32_t* tlwe_key) {
+    File f(fopen(path, "wb"));
+    if (!f) return RS_ERR_ARG;
+    bool ok = write_all(f.get(), kSecretMagic, 8) && write_all(f.get(), kParamBlock, sizeof(kParamBlock)) &&
+              write_all(f.get(), lwe_key, rs::LWE_N * 4) && write_all(f.get(), tlwe_key, rs::N * 4);
+    return ok ? RS_OK : RS_ERR_STATE;
+}
+int rs_read_secret_key(const char* path, int32_t* lwe_key, int32_t* tlwe_key) {
+    File f(fopen(path, "rb"));
+    if (!f || !check_header(f.get(), kSecretMagic)) return RS_ERR_ARG;
+    return read_all(f.get(), lwe_key, rs::LWE_N * 4) && read_all(f.get(), tlwe_key, rs::N * 4) ? RS_OK : RS_ERR_STATE;
+}
+int rs_write_eval_key(const char* path, const uint32_t* bsk, const uint32_t* ksk) {
+    File f(fopen(path, "wb"));
+    if (!f) return RS_ERR_ARG;
+    bool ok = write_all(f.get(), kEvalMagic, 8) && write_all(f.get(), kParamBlock, sizeof(kParamBlock)) &&
+              write_all(f.get(), ksk, RS_KSK_WORDS * 4) && write_all(f.get(), bsk, RS_BSK_WORDS * 4);
+    return ok ? RS_OK : RS_ERR_STATE;
+}
+int rs_read_eval_key(const char* path, uint32_t* bsk, uint32_t* ksk) {
+    File f(fopen(path, "rb"));
+    if (!f || !check_header(f.get(), kEvalMagic)) return RS_ERR_ARG;
+    return read_all(f.get(), ksk, RS_KSK_WORDS * 4) && read_all(f.get(), bsk, RS_BSK_WORDS * 4) ? RS_OK : RS_ERR_STATE;
+}
+int rs_write_ctxt(const char* path, const uint32_t* ct, size_t count, double variance, int append) {
+    File f(fopen(path, append ? "ab" : "wb"));
+    if (!f) return RS_ERR_ARG;
+    for (size_t c = 0; c < count; c++)
+        if (!write_all(f.get(), ct + c * rs::LWE_WORDS, rs::LWE_WORDS * 4) || !write_all(f.get(), &variance, 8)) return RS_ERR_STATE;
+    return RS_OK;
+}
+int rs_read_ctxt(const char* path, uint32_t* ct, size_t count) {
+    File f(fopen(path, "rb"));
+    if (!f) return RS_ERR_ARG;
+    double variance;
+    for (size_t c = 0; c < count; c++)
+        if (!read_all(f.get(), ct + c * rs::LWE_WORDS, rs::LWE_WORDS * 4) || !read_all(f.get(), &variance, 8)) return RS_ERR_STATE;
+    return RS_OK;
+}
+
+}  // extern "C"

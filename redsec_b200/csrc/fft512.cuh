@@ -20,10 +20,19 @@
 
 namespace rs {
 
-struct Twiddles {
+// COMPACT_H: keep only h[1], h[2], h[4] in registers and rebuild h[3,5,6,7] with 4 complex products per
+// transform (+16 DFMA, -16 registers); used by the 6-group variant whose budget is 168 registers/thread.
+template <bool COMPACT_H>
+struct TwiddlesT {
     double2 g[8];   // g[r]  = exp(i*pi*t*(1-4r)/1024)    (twist merged with pass-1 twiddle)
     double2 h[8];   // h[r2] = exp(-2*pi*i*t2*r2/64), t2 = t & 7   (h[0] = 1 unused)
 };
+template <>
+struct TwiddlesT<true> {
+    double2 g[8];
+    double2 h1, h2, h4;
+};
+using Twiddles = TwiddlesT<false>;
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -43,15 +52,32 @@ __device__ __forceinline__ void group_sync(int group) {  // named barrier over t
     asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory");
 }
 
-__device__ __forceinline__ void make_twiddles(Twiddles& tw, int t) {
+__device__ __forceinline__ double2 unit_root(double turns_times_two) {   // exp(i*pi*x)
+    double s, c;
+    sincospi(turns_times_two, &s, &c);
+    return make_double2(c, s);
+}
+__device__ __forceinline__ void make_twiddles(TwiddlesT<false>& tw, int t) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        double s, c;
-        sincospi((double)(t * (1 - 4 * r)) / 1024.0, &s, &c);
-        tw.g[r] = make_double2(c, s);
-        sincospi(-(double)((t & 7) * r) / 32.0, &s, &c);
-        tw.h[r] = make_double2(c, s);
+        tw.g[r] = unit_root((double)(t * (1 - 4 * r)) / 1024.0);
+        tw.h[r] = unit_root(-(double)((t & 7) * r) / 32.0);
     }
+}
+__device__ __forceinline__ void make_twiddles(TwiddlesT<true>& tw, int t) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) tw.g[r] = unit_root((double)(t * (1 - 4 * r)) / 1024.0);
+    tw.h1 = unit_root(-(double)(t & 7) / 32.0);
+    tw.h2 = unit_root(-(double)((t & 7) * 2) / 32.0);
+    tw.h4 = unit_root(-(double)((t & 7) * 4) / 32.0);
+}
+__device__ __forceinline__ void expand_h(double2 (&h)[8], const TwiddlesT<false>& tw) {
+#pragma unroll
+    for (int r = 1; r < 8; r++) h[r] = tw.h[r];
+}
+__device__ __forceinline__ void expand_h(double2 (&h)[8], const TwiddlesT<true>& tw) {
+    h[1] = tw.h1; h[2] = tw.h2; h[4] = tw.h4;
+    h[3] = cmul(tw.h1, tw.h2); h[5] = cmul(tw.h1, tw.h4); h[6] = cmul(tw.h2, tw.h4); h[7] = cmul(h[3], tw.h4);
 }
 
 // 8-point DFT in registers, W8 = exp(S*2*pi*i/8); natural order in, natural order out.
@@ -89,7 +115,8 @@ constexpr int FFT_BUF1 = 512;          // complex entries, exchange 1: [r][t]
 constexpr int FFT_BUF2 = 576;          // complex entries, exchange 2: [r][r2*9 + t2] (padded, conflict-free)
 
 // Forward transform.  In: v[q] = p[t+64q] + i*p[t+64q+512].  Out: v[r3] = Z[slot r3*64 + tid].
-__device__ __forceinline__ void fft512_fwd(double2 (&v)[8], const Twiddles& tw, double2* buf1, double2* buf2,
+template <class TW>
+__device__ __forceinline__ void fft512_fwd(double2 (&v)[8], const TW& tw, double2* buf1, double2* buf2,
                                            int t, int group) {
 #pragma unroll
     for (int q = 1; q < 8; q++) v[q] = cmul(v[q], twist_const(q));
@@ -102,8 +129,12 @@ __device__ __forceinline__ void fft512_fwd(double2 (&v)[8], const Twiddles& tw, 
     for (int q2 = 0; q2 < 8; q2++) v[q2] = buf1[rr * 64 + t2 + 8 * q2];
     dft8<-1>(v);
     buf2[rr * 72 + t2] = v[0];
+    {
+        double2 h[8];
+        expand_h(h, tw);
 #pragma unroll
-    for (int r2 = 1; r2 < 8; r2++) buf2[rr * 72 + r2 * 9 + t2] = cmul(v[r2], tw.h[r2]);
+        for (int r2 = 1; r2 < 8; r2++) buf2[rr * 72 + r2 * 9 + t2] = cmul(v[r2], h[r2]);
+    }
     group_sync(group);
     // thread v = r2' + 8*rr with r2' = t2 (same lane bits, different meaning)
 #pragma unroll
@@ -113,7 +144,8 @@ __device__ __forceinline__ void fft512_fwd(double2 (&v)[8], const Twiddles& tw, 
 
 // Inverse transform (scaled by 1/512).  In: v[r3] = A[slot r3*64 + tid].
 // Out: v[q] = z[t+64q] with Re -> coefficient t+64q, Im -> coefficient t+64q+512.
-__device__ __forceinline__ void fft512_inv(double2 (&v)[8], const Twiddles& tw, double2* buf1, double2* buf2,
+template <class TW>
+__device__ __forceinline__ void fft512_inv(double2 (&v)[8], const TW& tw, double2* buf1, double2* buf2,
                                            int t, int group) {
     const int t2 = t & 7, rr = t >> 3;
     dft8<+1>(v);
@@ -121,8 +153,12 @@ __device__ __forceinline__ void fft512_inv(double2 (&v)[8], const Twiddles& tw, 
     for (int x = 0; x < 8; x++) buf2[rr * 72 + t2 * 9 + x] = v[x];
     group_sync(group);
     v[0] = buf2[rr * 72 + t2];
+    {
+        double2 h[8];
+        expand_h(h, tw);
 #pragma unroll
-    for (int r2 = 1; r2 < 8; r2++) v[r2] = cmul_conj(buf2[rr * 72 + r2 * 9 + t2], tw.h[r2]);
+        for (int r2 = 1; r2 < 8; r2++) v[r2] = cmul_conj(buf2[rr * 72 + r2 * 9 + t2], h[r2]);
+    }
     dft8<+1>(v);
 #pragma unroll
     for (int q2 = 0; q2 < 8; q2++) buf1[rr * 64 + t2 + 8 * q2] = v[q2];
