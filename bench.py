@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (BASELINE.json: bootstrapped gates/sec per GPU).
+
+One step = one pass of the hot path over one batch: 2^16 independent bootstrapped gates (config[1]: NAND on even
+steps, XNOR on odd steps; reference keyset parameters), per GPU.  `value` times rs_gate_batch with inputs resident
+in HBM; `e2e` times the reference-facing host-buffer call rs_gate_batch_host (pinned host buffers, H2D + D2H inside
+the timed region).  `roofline` is the blind-rotation kernel against the FP64 roofline (258.4 MFLOP per bootstrap,
+SURVEY.md 8d) with the peak measured live by rs_fp64_peak (MEASURED_PEAKS.json carries no FP64 figure).
+`cpu_baseline` is the oracle's CPU port of the TFHE algorithm timed on the host cores (a reported baseline).
+
+  python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA path
+  python bench.py --impl reference [...]                     the CPU path only (oracle port; TFHE itself is not installable)
+Under torchrun (N>1) every rank runs its own 2^16-gate batch (weak scaling), time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GATES_PER_STEP = 1 << 16
+FLOP_PER_PBS = 258.4e6            # 350 x (22 x 26112 + 163840)
+BSK_FOURIER_BYTES = 114_688_000   # streamed once per wave of CTAs
+LWE_WIRE_BYTES = 351 * 4
+WORKLOAD = "gate microbench: 2^16 independent bootstrapped gates per step per GPU (NAND even steps / XNOR odd steps), keyset n=350 N=1024 l=10 Bgbit=3 t=9"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gates", type=int, default=GATES_PER_STEP, help="gates per step per GPU (default 2^16, the BASELINE config)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
+    ap.add_argument("--no-extra", action="store_true", help="skip the MNIST seconds/image side measurement")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); smax = float(r[1]); power.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c, p in zip(sm, power) if p > 300] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_baseline(ks, a, b, target_seconds: float, check_against=None) -> dict:
+    """Oracle port of the TFHE gate bootstrap on the host cores (bounded sample of the same workload)."""
+    from oracle import oracle as O
+    oks = O.KeySet(ks.lwe_key, ks.tlwe_key, ks.bsk, ks.ksk)
+    _ = oks.bsk_fft
+    threads = O.max_threads()
+    mu = 1 << 29
+    t0 = time.perf_counter()
+    O.gate("NAND", a[: 2 * threads], b[: 2 * threads], mu, oks)
+    probe = time.perf_counter() - t0
+    n = int(max(4 * threads, min(a.shape[0], 2 * threads * target_seconds / max(probe, 1e-3))))
+    n = (n // threads) * threads
+    t0 = time.perf_counter()
+    out = O.gate("NAND", a[:n], b[:n], mu, oks)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    O.gate("NAND", a[:2], b[:2], mu, oks, threads=1)
+    single = (time.perf_counter() - t1) / 2
+    res = {"value": n / dt, "unit": "gates/s", "cores": threads, "kind": "port",
+           "sample": f"{n} NAND gates of the step's batch, oracle FFT port (not the upstream TFHE binary), omp parallel for over gates",
+           "ms_per_gate_single_core": single * 1e3}
+    if check_against is not None:
+        res["sample_bit_exact_vs_gpu"] = bool(np.array_equal(out, check_against[:n]))
+    return res, n / dt
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the CPU implementation of the path (oracle port) with all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from redsec_b200 import client
+    from oracle import oracle as O
+    ks = client.keygen(0)
+    oks = O.KeySet(ks.lwe_key, ks.tlwe_key, ks.bsk, ks.ksk)
+    _ = oks.bsk_fft
+    threads = O.max_threads()
+    rng = np.random.default_rng(1)
+    n = max(2 * threads, 16)
+    a = client.encrypt_bits(rng.integers(0, 2, n), ks.lwe_key, seed=11)
+    b = client.encrypt_bits(rng.integers(0, 2, n), ks.lwe_key, seed=12)
+    t0 = time.perf_counter(); O.gate("NAND", a, b, 1 << 29, oks); probe = time.perf_counter() - t0
+    budget = 150.0 / max(args.steps + args.warmup, 1)               # whole run within a few minutes
+    per_step = int(max(threads, min(4096, n * min(budget, 20.0) / max(probe, 1e-3))))
+    per_step = max(threads, (per_step // threads) * threads)
+    a = client.encrypt_bits(rng.integers(0, 2, per_step), ks.lwe_key, seed=13)
+    b = client.encrypt_bits(rng.integers(0, 2, per_step), ks.lwe_key, seed=14)
+    for s in range(args.warmup):
+        O.gate("NAND" if s % 2 == 0 else "XNOR", a, b, 1 << 29, oks)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        O.gate("NAND" if s % 2 == 0 else "XNOR", a, b, 1 << 29, oks)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"{per_step} gates per step (bounded sample of the 2^16-gate batch), oracle FFT port of the TFHE algorithm, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "bootstrapped_gates_per_sec", "value": value, "unit": "gates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_gates_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "gates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import redsec_b200 as rs
+    from redsec_b200 import client
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    eng = rs.Engine(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)          # our kernels run on a stream torch events can see
+    ks = client.keygen(0)
+    eng.load_eval_key(ks.bsk, ks.ksk)
+    fp64_peak = eng.fp64_peak_tflops()
+
+    G = args.gates
+    rng = np.random.default_rng(1 + rank)        # i.i.d. Bernoulli(1/2) inputs, alpha = 2^-25
+    a_bits, b_bits = rng.integers(0, 2, G), rng.integers(0, 2, G)
+    a = client.encrypt_bits(a_bits, ks.lwe_key, seed=100 + rank)
+    b = client.encrypt_bits(b_bits, ks.lwe_key, seed=200 + rank)
+    mu = client.EIGHTH
+    d_a, d_b, d_out = eng.upload(a), eng.upload(b), eng.alloc(G)
+    ops = ["NAND", "XNOR"]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (`value`)
+    for s in range(args.warmup):
+        eng.gate(ops[s % 2], d_a, d_b, mu, d_out)
+    eng.sync()
+    sampler = ClockSampler(local_rank)
+    eng.profile(True); eng.profile_reset()
+    launches0 = eng.launch_count()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for s in range(args.steps):
+            eng.gate(ops[s % 2], d_a, d_b, mu, d_out)
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    br_ms, br_n = eng.profile_get(rs.engine.K_BLIND_ROTATE)
+    ks_ms, ks_n = eng.profile_get(rs.engine.K_KEYSWITCH)
+    lin_ms, lin_n = eng.profile_get(rs.engine.K_LINEAR)
+    eng.profile(False)
+    last_op = ops[(args.steps - 1) % 2]
+    out_dev = eng.download(d_out)
+
+    # ---- correctness of what was timed: truth table of every gate of the last step (product decrypt)
+    truth = (1 - (a_bits & b_bits)) if last_op == "NAND" else (1 - (a_bits ^ b_bits))
+    verified = bool(np.array_equal(client.decrypt_bits(out_dev, ks.lwe_key), truth))
+
+    # ---- end-to-end timing through the host-buffer C-ABI call (`e2e`): pinned host buffers, H2D + D2H in the region
+    h_a = torch.from_numpy(a).pin_memory(); h_b = torch.from_numpy(b).pin_memory()
+    h_out = torch.empty((G, 351), dtype=torch.int32).pin_memory()
+    na, nb, nout = h_a.numpy(), h_b.numpy(), h_out.numpy()
+    eng.gate_host(ops[0], na, nb, mu, nout)
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for s in range(args.steps):
+        eng.gate_host(ops[s % 2], na, nb, mu, nout)      # synchronous: returns when the result is in host memory
+    e3.record(stream)
+    barrier()
+    e2e_ms = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3 * 0.0)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, 0.0)
+    e2e_verified = bool(np.array_equal(nout.view(np.uint32), out_dev)) if last_op == ops[(args.steps - 1) % 2] else None
+
+    # max over ranks (device time)
+    t = torch.tensor([ms, e2e_wall_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        extra = mnist_seconds_per_image(eng, ks, client)
+
+    cpu = None
+    if rank == 0 and world >= 1:
+        cpu, _ = cpu_baseline(ks, a, b, args.cpu_seconds, check_against=(out_dev if last_op == "NAND" else None))
+
+    if rank == 0:
+        total_gates = world * G * args.steps
+        value = total_gates / (ms_max * 1e-3)
+        br_avg_s = br_ms / max(br_n, 1) * 1e-3
+        achieved_tflops = FLOP_PER_PBS * G / br_avg_s / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if tj.get("gates_per_launch") == G:
+                    traffic = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        peaks = {}
+        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp):
+            peaks = json.load(open(mp))
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": "bootstrapped_gates_per_sec", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "gates_per_step_per_gpu": G, "per_gpu_gates_per_sec": value / world,
+                       "l2": "inputs (2 x 92 MB of LWE rows) + 115 MB Fourier BSK + 104 MB KSK exceed the 126 MB L2; no explicit flush",
+                       "keyset": "redsec_params_small_v2, product keygen seed 0", "verified_truth_table": verified,
+                       "e2e_matches_device_path": e2e_verified},
+            "e2e": {"value": total_gates / (e2e_ms_max * 1e-3), "unit": "gates/s", "h2d_bytes_per_step": 2 * G * LWE_WIRE_BYTES,
+                    "d2h_bytes_per_step": G * LWE_WIRE_BYTES, "api": "rs_gate_batch_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / fp64_peak, "traffic": traffic,
+                         "kernel": "blind_rotate_kernel", "launch_ms": br_avg_s * 1e3, "launches": int(br_n),
+                         "algorithmic_flop_per_launch": FLOP_PER_PBS * G,
+                         "peak_source": "measured live by rs_fp64_peak (dependent-free DFMA loop, all SMs); MEASURED_PEAKS.json has no FP64 figure",
+                         "hbm": {"algorithmic_bytes_per_launch": BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4),
+                                 "achieved_gbs": (BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4)) / br_avg_s / 1e9,
+                                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+                         "step_share": {"blind_rotate_ms": br_ms / args.steps, "keyswitch_ms": ks_ms / args.steps,
+                                        "linear_ms": lin_ms / args.steps}},
+            "cpu_baseline": cpu,
+        }
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def mnist_seconds_per_image(eng, ks, client) -> dict:
+    """Side measurement (not the headline): encrypted inference time of nets/mnist/sign1024x1 on one GPU, activations resident."""
+    try:
+        from redsec_b200 import netspec, nets
+        spec = netspec.NETS["mnist/sign1024x1"]()
+        label, px = netspec.load_image_csv(spec["image"])
+        ct = client.encrypt_image(px, ks.lwe_key, seed=7)
+        net = nets.EncryptedNet(eng, spec)
+        d = eng.upload(ct)
+        out = net.run(d); eng.sync()
+        t0 = time.perf_counter()
+        out = net.run(d); eng.sync()
+        dt = time.perf_counter() - t0
+        scores = client.decrypt(eng.download(out), ks.lwe_key, 4096)
+        net.close()
+        return {"mnist_sign1024x1_s_per_image": dt, "bootstraps": 1220, "argmax": int(np.argmax(scores)), "label": int(label)}
+    except Exception as e:   # the side measurement must never break the headline line
+        return {"mnist_error": str(e)[:200]}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,10 +101,66 @@ int rs_ext_download(rs_ctx *ctx, uint32_t *host /*[count][1025]*/, const uint32_
  * (lib/GPU/gates.cu:158-202).  rowptr/col/sign/bias are DEVICE pointers (uploaded once in prep). */
 int rs_lwe_lincomb(rs_ctx *ctx, uint32_t *out_dev, size_t out_count, const uint32_t *in_dev, const int32_t *rowptr_dev,
                    const int32_t *col_dev, const int8_t *sign_dev, const uint32_t *bias_dev /* may be NULL */);
+/* ternary convolution / fully-connected layer on LWE rows; replaces {Bin,Int}Func::Convolution::execute
+ * (lib/BinFunc.cpp:142-330, lib/IntFunc.cpp:152-319; GPU twin lib/GPU/BinFunc_gpu.cu:110-222).  Activations are
+ * (h,w,c) c-fastest (lib/BinFunc.cpp:404).  wpacked_dev: weights in {-1,0,+1} packed [ceil(out_dep/16)][K][16] int8 with
+ * K index (fh*win_w+fw)*in_dep+di (the reference filter index lib/BinFunc.cpp:388-391 is k*OutDepth+od).
+ * int_mode=1: zero weights and padding contribute -1/4096 (lib/IntFunc.cpp:268,277) instead of 0.
+ * [od_begin,od_end) selects the output-channel slice this call computes (neuron sharding);
+ * out rows are [pixel][od-od_begin]. */
+typedef struct rs_conv_desc {
+    int32_t in_h, in_w, in_dep;
+    int32_t out_h, out_w, out_dep;
+    int32_t win_h, win_w, stride_h, stride_w, ofs_h, ofs_w;
+    int32_t int_mode;
+    int32_t od_begin, od_end;
+} rs_conv_desc;
+int rs_lwe_conv(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *in_dev, const int8_t *wpacked_dev,
+                const uint32_t *bias_dev /* [out_dep] torus32, may be NULL */, const rs_conv_desc *desc);
 int rs_dev_alloc(rs_ctx *ctx, size_t bytes, void **dev_out);
 int rs_dev_free(rs_ctx *ctx, void *dev);
 int rs_dev_upload(rs_ctx *ctx, void *dev, const void *host, size_t bytes);
 int rs_dev_download(rs_ctx *ctx, void *host, const void *dev, size_t bytes);
+
+/* restore canonical (pixel, channel) order after an all-gather of per-rank channel slices:
+ * in [world][pixels][c_local]  ->  out [pixels][world*c_local]   (SURVEY 8e exchange step) */
+int rs_lwe_interleave(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *gathered_dev, size_t pixels, int c_local, int world);
+
+/* -- client side (host C++) ------------------------------------------------------------
+ * replaces client/gen_secure_keyset.cpp:94-120, client/encrypt_image.cpp:65-85, client/decrypt_image.cpp:46-63 */
+uint32_t rs_modswitch_to_torus32(int32_t mu, int32_t msize);
+int32_t rs_modswitch_from_torus32(uint32_t phase, int32_t msize);
+int rs_keygen(uint64_t seed, int32_t *lwe_key /*[350]*/, int32_t *tlwe_key /*[1024]*/, uint32_t *bsk, uint32_t *ksk);
+int rs_lwe_encrypt(uint32_t *ct_wire, const uint32_t *mu, size_t count, double alpha, const int32_t *lwe_key, uint64_t seed);
+int rs_lwe_phase(uint32_t *phase, const uint32_t *ct_wire, size_t count, const int32_t *lwe_key);
+int rs_lwe_decrypt(int32_t *msg, const uint32_t *ct_wire, size_t count, const int32_t *lwe_key, int32_t msize);
+int rs_write_secret_key(const char *path, const int32_t *lwe_key, const int32_t *tlwe_key);
+int rs_read_secret_key(const char *path, int32_t *lwe_key, int32_t *tlwe_key);
+int rs_write_eval_key(const char *path, const uint32_t *bsk, const uint32_t *ksk);
+int rs_read_eval_key(const char *path, uint32_t *bsk, uint32_t *ksk);
+int rs_write_ctxt(const char *path, const uint32_t *ct_wire, size_t count, double variance, int append);
+int rs_read_ctxt(const char *path, uint32_t *ct_wire, size_t count);
+
+/* -- Layer forward: flat C view of the C++ classes in redsec_b200/host/redsec_layers.hpp ---
+ * which mirror IntLayer/BinLayer (lib/GPU/IntLayer.cuh:16-34, lib/GPU/BinLayer.cuh:16-34) and the generated
+ * HeBNN::init/run (nets/mnist/sign1024x1/net.cu).  Enum values are those of lib/Layer.h:58-101. */
+typedef struct rs_net rs_net;
+typedef struct rs_layer_params {    /* tNetParams, lib/Layer.h:126-167 */
+    int32_t conv_win_h, conv_win_w, conv_stride_h, conv_stride_w, conv_same_pad;
+    int32_t pool_win_h, pool_win_w, pool_stride_h, pool_stride_w, pool_same_pad;
+    int32_t e_bias, shift_bits, version;
+} rs_layer_params;
+rs_net *rs_net_create(rs_ctx *ctx);
+void rs_net_destroy(rs_net *net);
+int rs_net_add_layer(rs_net *net, int int_layer, int conv_type, int out_depth, int pool_type, int quant_type,
+                     const rs_layer_params *p);
+int rs_net_prep(rs_net *net, const char *weights_path /* var_prep.dat */, int in_h, int in_w, int in_dep);
+int rs_net_num_layers(const rs_net *net);
+int rs_net_layer_info(rs_net *net, int layer, size_t *out_count, int *channels, size_t *bootstraps, int *out_h, int *out_w);
+/* forward of one layer for rank's output-channel slice (world=1: whole layer).  Does not free in_dev; the caller
+ * frees *out_dev with rs_lwe_free.  Output rows are [pixel][ch_begin..ch_end). */
+int rs_net_layer_forward(rs_net *net, int layer, const uint32_t *in_dev, size_t in_count, int rank, int world,
+                         uint32_t **out_dev, size_t *out_count, int *ch_begin, int *ch_end);
 
 /* -- measurement ------------------------------------------------------------------------------------- */
 int rs_profile_enable(rs_ctx *ctx, int on);         /* bracket every kernel launch with CUDA events on the ctx stream */

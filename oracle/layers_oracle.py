@@ -1,0 +1,275 @@
+"""CPU restatement of REDsec's layer forward (plaintext twin and encrypted CPU path) -- TEST INFRASTRUCTURE ONLY.
+
+Follows the reference loops, not the product's kernels:
+  * weight file blocks      lib/BinOps_enc.cpp:247-297 (ternary: tag, MSB-first bits, sign then is_zero; ints: tag + int32)
+  * convolution             lib/BinFunc.cpp:142-330 / lib/IntFunc.cpp:152-319 (retrieve_dims :348-366, indices :388-404)
+  * sum pooling             lib/IntFunc.cpp:643-700, lib/BinFunc.cpp:677-732
+  * sign activation + bias  lib/BinFunc.cpp:1044-1075, lib/IntFunc.cpp:860-889; plaintext binarize lib/BinOps.cpp:207-217
+  * max pooling             lib/BinFunc.cpp:880-925 (as an OR tree at +-1/8, SURVEY.md H2 / defect R3)
+  * layer sequencing        lib/BinLayer.cpp:150-241, lib/IntLayer.cpp:153-235
+The plaintext path is pinned against the reference's own plaintext build (oracle/_ref, golden scores in
+tests/golden/ptxt_scores.json).  The encrypted path is "parity unpinned" like the rest of the oracle (no TFHE here).
+A net spec is plain data (see redsec_b200/netspec.py); it is passed in by the caller, this module imports nothing
+from the product.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle as O
+
+UNIT = 1 << 20      # 1/4096
+EIGHTH = 1 << 29    # 1/8
+
+
+# ----------------------------------------------------------------------------------------------- weight file
+def _read_ternary(buf: memoryview, pos: int, length: int):
+    tag = buf[pos]
+    assert tag in (1, 2), f"bad ternary tag {tag}"
+    nbits = 1 if tag == 1 else 2
+    nbytes = (length * nbits + 7) // 8
+    bits = np.unpackbits(np.frombuffer(buf[pos + 1: pos + 1 + nbytes], dtype=np.uint8))  # MSB first
+    if nbits == 1:
+        w = np.where(bits[:length] == 1, 1, -1)
+    else:
+        sign, zero = bits[0:2 * length:2], bits[1:2 * length:2]
+        w = np.where(zero == 1, 0, np.where(sign == 1, 1, -1))
+    return w.astype(np.int8), pos + 1 + nbytes
+
+
+def _read_ints(buf: memoryview, pos: int, length: int):
+    tag = buf[pos]
+    assert tag in (3, 4), f"bad int tag {tag}"
+    v = np.frombuffer(buf[pos + 1: pos + 1 + 4 * length], dtype="<i4").copy()
+    return v, pos + 1 + 4 * length
+
+
+def _same_out(n, stride):
+    return (n - 1) // stride + 1
+
+
+class PreparedLayer:
+    pass
+
+
+def prepare(spec: dict, weights_path: str):
+    """Dimension bookkeeping + weight loading (the E_PREP pass of {Bin,Int}Layer::run)."""
+    buf = memoryview(open(weights_path, "rb").read())
+    pos = 0
+    h, w, dep = spec["input"]
+    layers = []
+    for ls in spec["layers"]:
+        L = PreparedLayer()
+        L.spec = ls
+        conv = ls["conv"]
+        if conv in ("fc", "fc_final"):
+            dep, h, w = dep * h * w, 1, 1
+        L.has_conv = conv != "none"
+        if L.has_conv:
+            wh, ww = (1, 1) if conv.startswith("fc") else ls["conv_win"]
+            sh, sw = (1, 1) if conv.startswith("fc") else ls["conv_stride"]
+            same = True if conv.startswith("fc") else ls["conv_same_pad"]
+            L.cin = (h, w, dep)
+            if same:
+                oh, ow = _same_out(h, sh), _same_out(w, sw)
+                ofh = (wh - 1) // 2 if sh == 1 else (oh * sh - h) // 2
+                ofw = (ww - 1) // 2 if sw == 1 else (ow * sw - w) // 2
+            else:
+                ofh = ofw = 0
+                oh, ow = (h - 2 * ((wh - 1) // 2)) // sh, (w - 2 * ((ww - 1) // 2)) // sw
+            L.conv_geom = (wh, ww, sh, sw, ofh, ofw, oh, ow)
+            od = ls["depth"]
+            flat, pos = _read_ternary(buf, pos, wh * ww * dep * od)
+            L.weights = flat.reshape(wh, ww, dep, od)        # index ((fh*W+fw)*in_dep+di)*OutDepth+od
+            h, w, dep = oh, ow, od
+        L.has_sumpool = ls["pool"] == "sum"
+        if L.has_sumpool:
+            ph_, pw_ = ls["pool_win"]
+            sh, sw = ls["pool_stride"]
+            L.sp_in = (h, w)
+            if ls["pool_same_pad"]:
+                oh, ow = _same_out(h, sh), _same_out(w, sw)
+                ofh = (ph_ - 1) // 2 if sh == 1 else (oh * sh - h) // 2
+                ofw = (pw_ - 1) // 2 if sw == 1 else (ow * sw - w) // 2
+            else:
+                ofh = ofw = 0
+                oh, ow = (h - ph_ // 2 - 1) // sh + 1, (w - pw_ // 2 - 1) // sw + 1
+            L.sp_geom = (ph_, pw_, sh, sw, ofh, ofw, oh, ow)
+            h, w = oh, ow
+        L.q_dims = (h, w, dep)
+        L.bias, pos = _read_ints(buf, pos, dep)
+        if ls["act"] == "relu" and ls.get("e_bias") == 2:
+            _, pos = _read_ints(buf, pos, dep)
+        L.has_maxpool = ls["pool"] == "max" and ls["act"] == "sign" and conv != "fc_final"
+        if L.has_maxpool:
+            ph_, pw_ = ls["pool_win"]
+            sh, sw = ls["pool_stride"]
+            if ls["pool_same_pad"]:
+                oh, ow = _same_out(h, sh), _same_out(w, sw)
+            else:
+                oh, ow = h // ph_, w // pw_
+            L.mp_geom = (ph_, pw_, sh, sw, oh, ow)
+            h, w = oh, ow
+        L.out_dims = (h, w, dep)
+        layers.append(L)
+    assert pos == len(buf), f"weight file not consumed exactly: {pos} of {len(buf)}"
+    return layers
+
+
+# ----------------------------------------------------------------------------------------------- generic linear stage
+def _conv(L, x, zero_term, pad_term):
+    """x: [h][w][dep][...] array (ints or uint32 LWE rows).  Returns [oh][ow][od][...].
+    zero_term / pad_term: what a zero weight / padded position contributes (an array broadcastable to x[0,0,0])."""
+    wh, ww, sh, sw, ofh, ofw, oh, ow = L.conv_geom
+    h, w, dep = L.cin
+    od = L.weights.shape[3]
+    tail = x.shape[3:]
+    out = np.zeros((oh, ow, od) + tail, dtype=x.dtype)
+    wpos = (L.weights == 1)
+    wneg = (L.weights == -1)
+    wzero = (L.weights == 0)
+    for ph in range(oh):
+        for pw in range(ow):
+            acc = np.zeros((od,) + tail, dtype=x.dtype)
+            for fh in range(wh):
+                iy = fh + ph * sh - ofh
+                for fw in range(ww):
+                    ix = fw + pw * sw - ofw
+                    if not (0 <= iy < h and 0 <= ix < w):       # oob (same padding)
+                        if pad_term is not None:
+                            acc += (dep * pad_term).astype(x.dtype)
+                        continue
+                    v = x[iy, ix]                                 # [dep][...]
+                    P = wpos[fh, fw].astype(x.dtype)              # [dep][od]
+                    M = wneg[fh, fw].astype(x.dtype)
+                    if v.ndim == 1:
+                        acc += P.T @ v - M.T @ v
+                    else:
+                        acc += P.T @ v - M.T @ v                  # uint32 wraps mod 2^32
+                    if zero_term is not None:
+                        nz = wzero[fh, fw].sum(axis=0).astype(x.dtype)   # zero weights per od
+                        acc += nz.reshape((od,) + (1,) * len(tail)) * zero_term
+            out[ph, pw] = acc
+    return out
+
+
+def _sumpool(L, x):
+    ph_, pw_, sh, sw, ofh, ofw, oh, ow = L.sp_geom
+    h, w = L.sp_in
+    out = np.zeros((oh, ow) + x.shape[2:], dtype=x.dtype)
+    for a in range(oh):
+        for b in range(ow):
+            for fh in range(ph_):
+                iy = a * sh - ofh + fh
+                if not 0 <= iy < h:
+                    continue
+                for fw in range(pw_):
+                    ix = b * sw - ofw + fw
+                    if 0 <= ix < w:
+                        out[a, b] += x[iy, ix]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- plaintext twin
+def plain_forward(layers, pixels, enc_conv_semantics=False, collect=None):
+    """Plaintext twin (lib/unenc).  pixels: flat (h,w,c) ints already mapped x=2p-255.  Returns class scores.
+    enc_conv_semantics: apply the encrypted IntFunc convention (zero weight / padding contribute -1,
+    lib/IntFunc.cpp:268,277) instead of the plaintext one (0), for builder-defined integer conv layers."""
+    x = np.asarray(pixels, dtype=np.int64)
+    for L in layers:
+        ls = L.spec
+        if ls["kind"] == "bin":
+            x = 2 * x - 1                                 # bits 0/1 -> -1/+1 (lib/BinFunc.cpp:248,261)
+        if not L.has_conv:
+            x = x.reshape((L.sp_in if L.has_sumpool else L.q_dims[:2]) + (L.q_dims[2],))
+        if L.has_conv:
+            x = x.reshape(L.cin)
+            int_mode = ls["kind"] == "int" and enc_conv_semantics
+            term = np.int64(-1) if int_mode else None
+            x = _conv(L, x, term, term)
+        if L.has_sumpool:
+            x = _sumpool(L, x)
+        x = x + L.bias.astype(np.int64)
+        if ls["act"] == "none":
+            return x.reshape(-1)
+        x = (x >= 0).astype(np.int64)                    # binarize: val<0 -> 0 else 1
+        if L.has_maxpool:
+            ph_, pw_, sh, sw, oh, ow = L.mp_geom
+            y = np.zeros((oh, ow, x.shape[2]), dtype=np.int64)
+            for a in range(oh):
+                for b in range(ow):
+                    y[a, b] = x[a * sh: a * sh + ph_, b * sw: b * sw + pw_].reshape(-1, x.shape[2]).max(axis=0)
+            x = y
+        if collect is not None:
+            collect.append(x.copy())
+        x = x.reshape(-1)
+    return x
+
+
+# ----------------------------------------------------------------------------------------------- encrypted CPU path
+def enc_linear(L, ct):
+    """Bootstrap-free part of one layer on LWE rows [count][351] -> [(h,w,c) flat][351] (uint32 wrap-around)."""
+    ls = L.spec
+    x = np.ascontiguousarray(ct, dtype=np.uint32)
+    if L.has_conv:
+        x = x.reshape(L.cin + (O.LWE_WORDS,))
+        term = None
+        if ls["kind"] == "int":                         # trivial sample (0, -1/4096)
+            term = np.zeros(O.LWE_WORDS, dtype=np.uint32)
+            term[O.n] = (-UNIT) & 0xFFFFFFFF
+        x = _conv(L, x, term, term)
+    if L.has_sumpool:
+        if not L.has_conv:
+            x = x.reshape(L.sp_in + (L.q_dims[2], O.LWE_WORDS))
+        x = _sumpool(L, x)
+    x = x.reshape(L.q_dims + (O.LWE_WORDS,)).copy()
+    x[..., O.n] += (L.bias.astype(np.int64) * UNIT & 0xFFFFFFFF).astype(np.uint32)[None, None, :]
+    return x.reshape(-1, O.LWE_WORDS)
+
+
+def enc_layer_forward(L, ct, ks, threads=0):
+    """One encrypted layer: linear part, one sign bootstrap per neuron, max-pool OR tree."""
+    lin = enc_linear(L, ct)
+    if L.spec["act"] == "none":
+        return lin
+    if not L.has_maxpool:
+        return O.pbs(lin, UNIT, ks, threads=threads)
+    bits = O.pbs(lin, EIGHTH, ks, threads=threads).reshape(L.q_dims + (O.LWE_WORDS,))
+    ph_, pw_, sh, sw, oh, ow = L.mp_geom
+    assert (ph_, pw_) == (2, 2), "oracle OR tree restated for the 2x2 windows the shipped nets use"
+    a = bits[0:oh * sh:sh, 0:ow * sw:sw].reshape(-1, O.LWE_WORDS)
+    b = bits[0:oh * sh:sh, 1:ow * sw:sw].reshape(-1, O.LWE_WORDS)
+    c = bits[1:oh * sh:sh, 0:ow * sw:sw].reshape(-1, O.LWE_WORDS)
+    d = bits[1:oh * sh:sh, 1:ow * sw:sw].reshape(-1, O.LWE_WORDS)
+    # window element order (fh,fw) = (0,0),(0,1),(1,0),(1,1): level 1 pairs (0,1) and (2,3); level 2 emits +-1/4096
+    top = O.gate("OR", a, b, EIGHTH, ks, threads=threads)
+    bot = O.gate("OR", c, d, EIGHTH, ks, threads=threads)
+    return O.gate("OR", top, bot, UNIT, ks, threads=threads)
+
+
+def enc_forward(layers, ct, ks, threads=0, collect=None):
+    x = ct
+    for L in layers:
+        x = enc_layer_forward(L, x, ks, threads)
+        if collect is not None:
+            collect.append(x.copy())
+    return x
+
+
+def encode_pixels(pixels):
+    """client/encrypt_image.cpp:76: ptxt = 2*pixel - 255, mu = modSwitchToTorus32(ptxt, 4096)."""
+    v = 2 * np.asarray(pixels, dtype=np.int64) - 255
+    return (v * UNIT) & 0xFFFFFFFF
+
+
+def count_bootstraps(layers):
+    n = 0
+    for L in layers:
+        if L.spec["act"] != "sign":
+            continue
+        h, w, d = L.q_dims
+        n += h * w * d
+        if L.has_maxpool:
+            oh, ow = L.mp_geom[4], L.mp_geom[5]
+            n += 3 * oh * ow * d
+    return n

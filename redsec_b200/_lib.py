@@ -40,6 +40,27 @@ SIGNATURES = {
     "rs_dev_free": (C.c_int, [vp, vp]),
     "rs_dev_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "rs_dev_download": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_lwe_conv": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+    "rs_lwe_interleave": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_int, C.c_int]),
+    "rs_modswitch_to_torus32": (C.c_uint32, [C.c_int32, C.c_int32]),
+    "rs_modswitch_from_torus32": (C.c_int32, [C.c_uint32, C.c_int32]),
+    "rs_keygen": (C.c_int, [C.c_uint64, vp, vp, vp, vp]),
+    "rs_lwe_encrypt": (C.c_int, [vp, vp, C.c_size_t, C.c_double, vp, C.c_uint64]),
+    "rs_lwe_phase": (C.c_int, [vp, vp, C.c_size_t, vp]),
+    "rs_lwe_decrypt": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_int32]),
+    "rs_write_secret_key": (C.c_int, [C.c_char_p, vp, vp]),
+    "rs_read_secret_key": (C.c_int, [C.c_char_p, vp, vp]),
+    "rs_write_eval_key": (C.c_int, [C.c_char_p, vp, vp]),
+    "rs_read_eval_key": (C.c_int, [C.c_char_p, vp, vp]),
+    "rs_write_ctxt": (C.c_int, [C.c_char_p, vp, C.c_size_t, C.c_double, C.c_int]),
+    "rs_read_ctxt": (C.c_int, [C.c_char_p, vp, C.c_size_t]),
+    "rs_net_create": (vp, [vp]),
+    "rs_net_destroy": (None, [vp]),
+    "rs_net_add_layer": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "rs_net_prep": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "rs_net_num_layers": (C.c_int, [vp]),
+    "rs_net_layer_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rs_net_layer_forward": (C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rs_profile_enable": (C.c_int, [vp, C.c_int]),
     "rs_profile_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "rs_profile_reset": (C.c_int, [vp]),

@@ -389,6 +389,42 @@ int rs_lwe_lincomb(rs_ctx* ctx, uint32_t* out_dev, size_t out_count, const uint3
     return RS_OK;
 }
 
+int rs_lwe_conv(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* in_dev, const int8_t* wpacked_dev, const uint32_t* bias_dev,
+                const rs_conv_desc* desc) {
+    if (!ctx || !out_dev || !in_dev || !wpacked_dev || !desc) return fail(ctx, RS_ERR_ARG, "rs_lwe_conv: NULL argument");
+    if (desc->od_begin % rs::CONV_OD_TILE != 0 || desc->od_end <= desc->od_begin || desc->od_end > desc->out_dep)
+        return fail(ctx, RS_ERR_ARG, "rs_lwe_conv: bad channel slice [%d,%d) of %d (begin must be a multiple of %d)", desc->od_begin,
+                    desc->od_end, desc->out_dep, rs::CONV_OD_TILE);
+    rs::ConvDesc d;
+    d.in_h = desc->in_h; d.in_w = desc->in_w; d.in_dep = desc->in_dep;
+    d.out_h = desc->out_h; d.out_w = desc->out_w; d.out_dep = desc->out_dep;
+    d.win_h = desc->win_h; d.win_w = desc->win_w; d.stride_h = desc->stride_h; d.stride_w = desc->stride_w;
+    d.ofs_h = desc->ofs_h; d.ofs_w = desc->ofs_w; d.od_begin = desc->od_begin; d.od_end = desc->od_end;
+    d.unit = 1u << 20;   // modSwitchToTorus32(1, 4096)
+    dim3 grid((unsigned)(d.out_h * d.out_w), (unsigned)((d.od_end - d.od_begin + rs::CONV_OD_TILE - 1) / rs::CONV_OD_TILE));
+    {
+        LaunchScope ls(ctx, RS_K_LINEAR);
+        if (desc->int_mode) rs::lwe_conv_kernel<true><<<grid, rs::CONV_THREADS, 0, ctx->stream>>>(out_dev, in_dev, wpacked_dev, bias_dev, d);
+        else rs::lwe_conv_kernel<false><<<grid, rs::CONV_THREADS, 0, ctx->stream>>>(out_dev, in_dev, wpacked_dev, bias_dev, d);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_lwe_interleave(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* gathered_dev, size_t pixels, int c_local, int world) {
+    if (!ctx || !out_dev || !gathered_dev || c_local <= 0 || world <= 0) return fail(ctx, RS_ERR_ARG, "rs_lwe_interleave: bad argument");
+    const size_t rows = pixels * (size_t)c_local * world;
+    if (rows == 0) return RS_OK;
+    const size_t cap = (size_t)ctx->sm_count * 32;
+    {
+        LaunchScope ls(ctx, RS_K_LINEAR);
+        rs::lwe_interleave_kernel<<<(unsigned)(rows < cap ? rows : cap), rs::LWE_STRIDE / 4, 0, ctx->stream>>>(
+            reinterpret_cast<uint4*>(out_dev), reinterpret_cast<const uint4*>(gathered_dev), pixels, c_local, world);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
 int rs_dev_alloc(rs_ctx* ctx, size_t bytes, void** dev_out) {
     if (!ctx || !dev_out) return fail(ctx, RS_ERR_ARG, "rs_dev_alloc: NULL argument");
     RS_CUDA(ctx, cudaSetDevice(ctx->device));

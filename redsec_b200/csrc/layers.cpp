@@ -1,0 +1,580 @@
+// redsec_b200/csrc/layers.cpp -- host-side Layer forward over the C-ABI.
+//
+// What the reference does per neuron / per gate (lib/BinFunc.cpp:1044-1075, lib/IntFunc.cpp:860-889,
+// lib/BinFunc.cpp:880-925, GPU twins lib/GPU/BinFunc_gpu.cu:465-531,591-629) this file does per layer:
+//   linear part (conv / FC / sum-pool / bias) -> ONE rs_pbs_batch over every neuron of the layer
+//   -> max-pool as an OR tree, one batched launch per tree level.
+// Host C++ only: every device operation is an rs_* call from include/redsec_b200.h.
+//
+// Encodings: bit b <-> torus +-1/4096; bias b <-> trivial LWE modSwitchToTorus32(b,4096)
+// (lib/BinOps_enc.cpp:292-295); sign activation = bootstrap with mu=1/4096 (lib/BinOps_enc.cpp:182-186).
+// Max-pool (reference defect R3): the reference ORs +-1/4096 bits with a gate that expects +-1/8,
+// starting from an uninitialised accumulator (lib/BinFunc.cpp:891,917).  Here the sign bootstrap in front of a
+// max-pool emits +-1/8, the OR tree runs at +-1/8 and its last level emits +-1/4096 again.
+#include <cassert>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+
+#include "../host/redsec_layers.hpp"
+
+namespace redsec {
+namespace {
+
+constexpr uint32_t kUnit = 1u << 20;        // 1/4096 on the torus
+constexpr uint32_t kEighth = 1u << 29;      // 1/8
+constexpr int kTile = 16;                   // CONV_OD_TILE of the conv kernel
+
+#define RS_TRY(call) do { int rc_ = (call); if (rc_ != RS_OK) return rc_; } while (0)
+
+struct Csr {   // host-side sparse rows: out[o] = (0,bias[o]) + sum w*in[col]
+    std::vector<int32_t> rowptr{0}, col;
+    std::vector<int8_t> w;
+    std::vector<uint32_t> bias;
+    void entry(int32_t c, int8_t weight) { col.push_back(c); w.push_back(weight); }
+    void end_row(uint32_t b) { rowptr.push_back((int32_t)col.size()); bias.push_back(b); }
+    size_t rows() const { return rowptr.size() - 1; }
+};
+
+struct DevCsr {
+    rs_ctx* ctx = nullptr;
+    void *rowptr = nullptr, *col = nullptr, *w = nullptr, *bias = nullptr;
+    size_t rows = 0;
+    DevCsr() = default;
+    DevCsr(const DevCsr&) = delete;
+    DevCsr& operator=(const DevCsr&) = delete;
+    ~DevCsr() { release(); }
+    void release() {
+        if (!ctx) return;
+        rs_dev_free(ctx, rowptr); rs_dev_free(ctx, col); rs_dev_free(ctx, w); rs_dev_free(ctx, bias);
+        rowptr = col = w = bias = nullptr;
+    }
+    int upload(rs_ctx* c, const Csr& h) {
+        release();
+        ctx = c; rows = h.rows();
+        auto up = [&](void** dst, const void* src, size_t bytes) -> int {
+            RS_TRY(rs_dev_alloc(ctx, bytes ? bytes : 4, dst));
+            if (bytes) RS_TRY(rs_dev_upload(ctx, *dst, src, bytes));
+            return RS_OK;
+        };
+        RS_TRY(up(&rowptr, h.rowptr.data(), h.rowptr.size() * 4));
+        RS_TRY(up(&col, h.col.data(), h.col.size() * 4));
+        RS_TRY(up(&w, h.w.data(), h.w.size()));
+        RS_TRY(up(&bias, h.bias.data(), h.bias.size() * 4));
+        return RS_OK;
+    }
+    int apply(uint32_t* out, const uint32_t* in) const {
+        return rs_lwe_lincomb(ctx, out, rows, in, (const int32_t*)rowptr, (const int32_t*)col, (const int8_t*)w, (const uint32_t*)bias);
+    }
+};
+
+// one max-pool tree level: rows reading the tree buffer, bootstrapped with mu
+struct PoolStep {
+    DevCsr csr;
+    size_t dst_offset = 0;    // row offset in the tree buffer where the bootstrapped results land
+    uint32_t mu = kEighth;
+};
+
+struct PoolPlan {   // OR tree for one channel count
+    std::vector<std::unique_ptr<PoolStep>> steps;
+    size_t in_count = 0, buf_count = 0, out_count = 0;
+    DevCsr final_gather;      // tree buffer -> canonical (oph,opw,c) order
+    size_t gates = 0;
+};
+
+struct ConvWeights { void* packed = nullptr; void* bias = nullptr; };
+
+int out_extent_same(int in, int stride) { return (in - 1) / stride + 1; }
+
+}  // namespace
+
+class LayerImpl {
+public:
+    rs_ctx* ctx;
+    bool int_inputs;
+    eConvType ec; uint16_t depth; ePoolType ep; eQuantType eq;
+    tNetParams np;
+    bool prepared = false;
+    // conv geometry (after the FC flatten)
+    bool has_conv = false;
+    int cin_h = 0, cin_w = 0, cin_dep = 0, cout_h = 0, cout_w = 0, cout_dep = 0, ofs_h = 0, ofs_w = 0;
+    std::vector<int8_t> weights;        // [K][cout_dep] in {-1,0,1}, K = (fh*win_w+fw)*cin_dep+di
+    // sum-pool geometry
+    bool has_sumpool = false;
+    int sp_in_h = 0, sp_in_w = 0, sp_out_h = 0, sp_out_w = 0, sp_ofs_h = 0, sp_ofs_w = 0;
+    // quantize
+    int q_h = 0, q_w = 0, q_dep = 0;    // dims at the activation
+    std::vector<uint32_t> bias_torus;   // [q_dep]
+    // max-pool geometry
+    bool has_maxpool = false;
+    int mp_out_h = 0, mp_out_w = 0;
+    // caches keyed by channel slice
+    std::map<std::pair<int, int>, ConvWeights> conv_cache;
+    std::map<std::pair<int, int>, std::unique_ptr<DevCsr>> sumpool_cache, identity_cache;
+    std::map<int, std::unique_ptr<PoolPlan>> maxpool_cache;
+
+    ~LayerImpl() {
+        for (auto& kv : conv_cache) { rs_dev_free(ctx, kv.second.packed); rs_dev_free(ctx, kv.second.bias); }
+    }
+
+    int channels() const { return q_dep; }
+    size_t final_h() const { return has_maxpool ? mp_out_h : q_h; }
+    size_t final_w() const { return has_maxpool ? mp_out_w : q_w; }
+
+    // ---- weight file blocks (readers lib/BinOps_enc.cpp:247-297)
+    static int read_ternary(FILE* fd, std::vector<int8_t>& out, size_t len) {
+        uint8_t tag = 0;
+        if (fread(&tag, 1, 1, fd) != 1 || (tag != 1 && tag != 2)) return RS_ERR_ARG;
+        const int nbits = tag == 1 ? 1 : 2;
+        std::vector<uint8_t> packed((len * nbits + 7) / 8);
+        if (fread(packed.data(), 1, packed.size(), fd) != packed.size()) return RS_ERR_ARG;
+        out.resize(len);
+        for (size_t i = 0; i < len; i++) {
+            const size_t bit = i * nbits;
+            const int sign = (packed[bit >> 3] >> (7 - (bit & 7))) & 1;               // MSB first: 1 -> +1, 0 -> -1
+            int zero = 0;
+            if (nbits == 2) zero = (packed[(bit + 1) >> 3] >> (7 - ((bit + 1) & 7))) & 1;
+            out[i] = zero ? 0 : (sign ? 1 : -1);
+        }
+        return RS_OK;
+    }
+    static int read_ints(FILE* fd, std::vector<int32_t>& out, size_t len) {
+        uint8_t tag = 0;
+        if (fread(&tag, 1, 1, fd) != 1 || (tag != 3 && tag != 4)) return RS_ERR_ARG;
+        out.resize(len);
+        return fread(out.data(), 4, len, fd) == len ? RS_OK : RS_ERR_ARG;
+    }
+
+    // ---- prep: dimension bookkeeping of {Bin,Int}Layer::run(E_PREP) (lib/BinLayer.cpp:150-241, lib/IntLayer.cpp:153-235)
+    int prep(FILE* fd, tDimensions* dim) {
+        if (prepared || !fd || !dim) return RS_ERR_ARG;
+        if (ec == E_FC || ec == E_FC_FINAL) {   // flatten (lib/BinLayer.cpp:157-167)
+            dim->in_dep *= (uint32_t)dim->hw.h * dim->hw.w;
+            dim->hw.h = 1; dim->hw.w = 1;
+        }
+        if (ec != E_NO_CONV) {
+            has_conv = true;
+            const tConvParams& cv = np.conv;
+            cin_h = dim->hw.h; cin_w = dim->hw.w; cin_dep = (int)dim->in_dep; cout_dep = depth;
+            if (cv.same_pad) {   // lib/BinFunc.cpp:87-95
+                cout_h = out_extent_same(cin_h, cv.stride.h); cout_w = out_extent_same(cin_w, cv.stride.w);
+                ofs_h = cv.stride.h == 1 ? (cv.window.h - 1) / 2 : (cout_h * cv.stride.h - cin_h) / 2;
+                ofs_w = cv.stride.w == 1 ? (cv.window.w - 1) / 2 : (cout_w * cv.stride.w - cin_w) / 2;
+            } else {             // lib/BinFunc.cpp:96-104
+                ofs_h = ofs_w = 0;
+                cout_h = (cin_h - 2 * ((cv.window.h - 1) / 2)) / cv.stride.h;
+                cout_w = (cin_w - 2 * ((cv.window.w - 1) / 2)) / cv.stride.w;
+            }
+            const size_t K = (size_t)cv.window.h * cv.window.w * cin_dep;
+            RS_TRY(read_ternary(fd, weights, K * cout_dep));
+            dim->up_bound *= (uint32_t)(dim->filter_bits * cv.window.w * cv.window.h) * dim->in_dep;
+            for (dim->in_bits = dim->in_bits; (dim->up_bound >> dim->in_bits) > 0; dim->in_bits++) {}
+            dim->hw.h = (int16_t)cout_h; dim->hw.w = (int16_t)cout_w; dim->in_dep = cout_dep;
+        }
+        if (ep == E_SUMPOOL) {   // lib/IntFunc.cpp:598-634
+            has_sumpool = true;
+            const tPoolParams& pl = np.pool;
+            sp_in_h = dim->hw.h; sp_in_w = dim->hw.w;
+            if (pl.same_pad) {
+                sp_out_h = out_extent_same(sp_in_h, pl.stride.h); sp_out_w = out_extent_same(sp_in_w, pl.stride.w);
+                sp_ofs_h = pl.stride.h == 1 ? (pl.window.h - 1) / 2 : (sp_out_h * pl.stride.h - sp_in_h) / 2;
+                sp_ofs_w = pl.stride.w == 1 ? (pl.window.w - 1) / 2 : (sp_out_w * pl.stride.w - sp_in_w) / 2;
+            } else {
+                sp_ofs_h = sp_ofs_w = 0;
+                sp_out_h = (sp_in_h - pl.window.h / 2 - 1) / pl.stride.h + 1;
+                sp_out_w = (sp_in_w - pl.window.w / 2 - 1) / pl.stride.w + 1;
+            }
+            dim->up_bound *= (uint32_t)(pl.window.w * pl.window.h);
+            dim->scale *= (float)(pl.window.w * pl.window.h);
+            dim->hw.h = (int16_t)sp_out_h; dim->hw.w = (int16_t)sp_out_w;
+        }
+        // quantize: bias block of length in_dep (lib/BinFunc.cpp:1001-1003)
+        q_h = dim->hw.h; q_w = dim->hw.w; q_dep = (int)dim->in_dep;
+        std::vector<int32_t> bias;
+        RS_TRY(read_ints(fd, bias, (size_t)q_dep));
+        bias_torus.resize(q_dep);
+        for (int i = 0; i < q_dep; i++) bias_torus[i] = (uint32_t)bias[i] * kUnit;   // modSwitchToTorus32(b, 4096)
+        if (eq == E_ACTIVATION_RELU && np.e_bias == E_BNORM) {   // slope block is present in the file; f4 is out of scope
+            std::vector<int32_t> slope;
+            RS_TRY(read_ints(fd, slope, (size_t)q_dep));
+        }
+        if (eq == E_ACTIVATION_SIGN) { dim->in_bits = 1; dim->up_bound = 1; dim->scale = 1.0f; }
+        dim->out_bits = SINGLE_BIT;
+        if (ep == E_MAXPOOL && eq == E_ACTIVATION_SIGN && ec != E_FC_FINAL) {   // lib/BinFunc.cpp:855-866
+            has_maxpool = true;
+            const tPoolParams& pl = np.pool;
+            if (pl.same_pad) { mp_out_h = out_extent_same(q_h, pl.stride.h); mp_out_w = out_extent_same(q_w, pl.stride.w); }
+            else { mp_out_h = q_h / pl.window.h; mp_out_w = q_w / pl.window.w; }
+            dim->hw.h = (int16_t)mp_out_h; dim->hw.w = (int16_t)mp_out_w;
+        }
+        prepared = true;
+        return RS_OK;
+    }
+
+    // ---- device tables, built lazily per output-channel slice [c0,c1)
+    int conv_tables(int c0, int c1, ConvWeights** out) {
+        auto key = std::make_pair(c0, c1);
+        auto it = conv_cache.find(key);
+        if (it == conv_cache.end()) {
+            const size_t K = (size_t)np.conv.window.h * np.conv.window.w * cin_dep;
+            const int cl = c1 - c0, tiles = (cl + kTile - 1) / kTile;
+            std::vector<int8_t> packed((size_t)tiles * K * kTile, 0);
+            for (int t = 0; t < tiles; t++)
+                for (size_t k = 0; k < K; k++)
+                    for (int o = 0; o < kTile; o++) {
+                        const int od = c0 + t * kTile + o;
+                        if (od < c1) packed[((size_t)t * K + k) * kTile + o] = weights[k * cout_dep + od];
+                    }
+            ConvWeights cw;
+            RS_TRY(rs_dev_alloc(ctx, packed.size(), &cw.packed));
+            RS_TRY(rs_dev_upload(ctx, cw.packed, packed.data(), packed.size()));
+            if (!has_sumpool) {   // bias rides on the conv when nothing linear follows it
+                RS_TRY(rs_dev_alloc(ctx, (size_t)cl * 4, &cw.bias));
+                RS_TRY(rs_dev_upload(ctx, cw.bias, bias_torus.data() + c0, (size_t)cl * 4));
+            }
+            it = conv_cache.emplace(key, cw).first;
+        }
+        *out = &it->second;
+        return RS_OK;
+    }
+
+    // sum-pool over a local channel slice; rows (oph,opw,cl), inputs (ih,iw,cl) (lib/IntFunc.cpp:665-697)
+    int sumpool_table(int c0, int c1, DevCsr** out) {
+        auto key = std::make_pair(c0, c1);
+        auto it = sumpool_cache.find(key);
+        if (it == sumpool_cache.end()) {
+            const tPoolParams& pl = np.pool;
+            const int cl = c1 - c0;
+            Csr csr;
+            for (int oph = 0; oph < sp_out_h; oph++)
+                for (int opw = 0; opw < sp_out_w; opw++)
+                    for (int c = 0; c < cl; c++) {
+                        const int ih0 = oph * pl.stride.h - sp_ofs_h, iw0 = opw * pl.stride.w - sp_ofs_w;
+                        for (int fh = 0; fh < pl.window.h && ih0 + fh < sp_in_h; fh++) {
+                            if (ih0 + fh < 0) continue;
+                            for (int fw = 0; fw < pl.window.w && iw0 + fw < sp_in_w; fw++) {
+                                if (iw0 + fw < 0) continue;
+                                csr.entry(((ih0 + fh) * sp_in_w + iw0 + fw) * cl + c, 1);
+                            }
+                        }
+                        csr.end_row(bias_torus[c0 + c]);
+                    }
+            auto dev = std::make_unique<DevCsr>();
+            RS_TRY(dev->upload(ctx, csr));
+            it = sumpool_cache.emplace(key, std::move(dev)).first;
+        }
+        *out = it->second.get();
+        return RS_OK;
+    }
+
+    // bias add only (E_NO_CONV without pooling, e.g. CIFAR layer 0); input (h,w,C), output slice (h,w,cl)
+    int identity_table(int c0, int c1, DevCsr** out) {
+        auto key = std::make_pair(c0, c1);
+        auto it = identity_cache.find(key);
+        if (it == identity_cache.end()) {
+            Csr csr;
+            for (int p = 0; p < q_h * q_w; p++)
+                for (int c = c0; c < c1; c++) { csr.entry(p * q_dep + c, 1); csr.end_row(bias_torus[c]); }
+            auto dev = std::make_unique<DevCsr>();
+            RS_TRY(dev->upload(ctx, csr));
+            it = identity_cache.emplace(key, std::move(dev)).first;
+        }
+        *out = it->second.get();
+        return RS_OK;
+    }
+
+    // OR tree over each pooling window for cl local channels (replaces the depth-4 chain of lib/BinFunc.cpp:896-919)
+    int maxpool_plan(int cl, PoolPlan** out) {
+        auto it = maxpool_cache.find(cl);
+        if (it == maxpool_cache.end()) {
+            const tPoolParams& pl = np.pool;
+            auto plan = std::make_unique<PoolPlan>();
+            const size_t n_out = (size_t)mp_out_h * mp_out_w * cl;
+            plan->in_count = (size_t)q_h * q_w * cl;
+            plan->out_count = n_out;
+            std::vector<std::vector<int32_t>> items(n_out);   // indices into the tree buffer
+            for (int oph = 0; oph < mp_out_h; oph++)
+                for (int opw = 0; opw < mp_out_w; opw++)
+                    for (int c = 0; c < cl; c++) {
+                        auto& v = items[((size_t)oph * mp_out_w + opw) * cl + c];
+                        const int ih0 = oph * pl.stride.h, iw0 = opw * pl.stride.w;   // offset_window is 0 (reference R4)
+                        for (int fh = 0; fh < pl.window.h && ih0 + fh < q_h; fh++)
+                            for (int fw = 0; fw < pl.window.w && iw0 + fw < q_w; fw++)
+                                v.push_back(((ih0 + fh) * q_w + iw0 + fw) * cl + c);
+                    }
+            size_t next = plan->in_count;
+            std::vector<int32_t> final_pos(n_out, -1);
+            bool more = true;
+            while (more) {
+                more = false;
+                Csr mid, fin;                 // OR gates whose result is reduced further / is the pooled bit
+                std::vector<size_t> fin_owner;
+                std::vector<std::pair<size_t, size_t>> mid_slots;   // (output, slot in its new item list)
+                std::vector<std::vector<int32_t>> nxt(n_out);
+                for (size_t o = 0; o < n_out; o++) {
+                    auto& v = items[o];
+                    if (final_pos[o] >= 0 || v.empty()) continue;
+                    if (v.size() == 1) {      // single element window: re-encode +-1/8 -> +-1/4096 with one bootstrap
+                        fin.entry(v[0], 1); fin.end_row(0); fin_owner.push_back(o);
+                        continue;
+                    }
+                    const bool last = v.size() == 2;
+                    for (size_t k = 0; k + 1 < v.size(); k += 2) {
+                        Csr& dst = last ? fin : mid;
+                        dst.entry(v[k], 1); dst.entry(v[k + 1], 1); dst.end_row(kEighth);   // OR: (0,1/8)+a+b
+                        if (last) fin_owner.push_back(o);
+                        else { mid_slots.push_back({o, nxt[o].size()}); nxt[o].push_back(-1); }
+                    }
+                    if (v.size() & 1) nxt[o].push_back(v.back());
+                }
+                plan->gates += mid.rows() + fin.rows();
+                if (mid.rows()) {
+                    auto st = std::make_unique<PoolStep>();
+                    RS_TRY(st->csr.upload(ctx, mid));
+                    st->dst_offset = next; st->mu = kEighth;
+                    for (size_t r = 0; r < mid_slots.size(); r++) nxt[mid_slots[r].first][mid_slots[r].second] = (int32_t)(next + r);
+                    next += mid.rows();
+                    plan->steps.push_back(std::move(st));
+                    more = true;
+                }
+                if (fin.rows()) {
+                    auto st = std::make_unique<PoolStep>();
+                    RS_TRY(st->csr.upload(ctx, fin));
+                    st->dst_offset = next; st->mu = kUnit;
+                    for (size_t r = 0; r < fin_owner.size(); r++) final_pos[fin_owner[r]] = (int32_t)(next + r);
+                    next += fin.rows();
+                    plan->steps.push_back(std::move(st));
+                }
+                for (size_t o = 0; o < n_out; o++) if (final_pos[o] < 0) items[o] = std::move(nxt[o]);
+            }
+            plan->buf_count = next;
+            Csr gather;
+            for (size_t o = 0; o < n_out; o++) { gather.entry(final_pos[o], 1); gather.end_row(0); }
+            RS_TRY(plan->final_gather.upload(ctx, gather));
+            it = maxpool_cache.emplace(cl, std::move(plan)).first;
+        }
+        *out = it->second.get();
+        return RS_OK;
+    }
+
+    // ---- forward for the channel slice [c0,c1); does not free `in`
+    int forward(const Batch& in, int c0, int c1, Batch* out) {
+        if (!prepared) return RS_ERR_STATE;
+        if (eq == E_ACTIVATION_RELU) return RS_ERR_STATE;   // DoReFa ReLU path (f4) is not part of this engine
+        const int cl = c1 - c0;
+        uint32_t* cur = nullptr;       // linear-part result, rows (h,w,cl)
+        size_t cur_count = 0;
+        auto alloc = [&](size_t count, uint32_t** p) { return rs_lwe_alloc(ctx, count, p); };
+
+        if (has_conv) {
+            if (in.count != (size_t)cin_h * cin_w * cin_dep) return RS_ERR_ARG;
+            ConvWeights* cw = nullptr;
+            RS_TRY(conv_tables(c0, c1, &cw));
+            rs_conv_desc d{};
+            d.in_h = cin_h; d.in_w = cin_w; d.in_dep = cin_dep; d.out_h = cout_h; d.out_w = cout_w; d.out_dep = cl;
+            d.win_h = np.conv.window.h; d.win_w = np.conv.window.w; d.stride_h = np.conv.stride.h; d.stride_w = np.conv.stride.w;
+            d.ofs_h = ofs_h; d.ofs_w = ofs_w; d.int_mode = int_inputs ? 1 : 0; d.od_begin = 0; d.od_end = cl;
+            cur_count = (size_t)cout_h * cout_w * cl;
+            RS_TRY(alloc(cur_count, &cur));
+            RS_TRY(rs_lwe_conv(ctx, cur, in.dev, (const int8_t*)cw->packed, (const uint32_t*)cw->bias, &d));
+        }
+        if (has_sumpool) {
+            DevCsr* sp = nullptr;
+            uint32_t* pooled = nullptr;
+            const uint32_t* src = cur;
+            if (!has_conv) {   // pooling the raw input: only the full channel range makes sense (in_dep is 1 or 3)
+                if (c0 != 0 || c1 != q_dep) return RS_ERR_ARG;
+                if (in.count != (size_t)sp_in_h * sp_in_w * q_dep) return RS_ERR_ARG;
+                src = in.dev;
+            }
+            RS_TRY(sumpool_table(c0, c1, &sp));
+            RS_TRY(alloc(sp->rows, &pooled));
+            RS_TRY(sp->apply(pooled, src));
+            if (cur) rs_lwe_free(ctx, cur);
+            cur = pooled; cur_count = sp->rows;
+        }
+        if (!has_conv && !has_sumpool) {
+            if (in.count != (size_t)q_h * q_w * q_dep) return RS_ERR_ARG;
+            DevCsr* id = nullptr;
+            RS_TRY(identity_table(c0, c1, &id));
+            cur_count = id->rows;
+            RS_TRY(alloc(cur_count, &cur));
+            RS_TRY(id->apply(cur, in.dev));
+        }
+        if (eq == E_ACTIVATION_NONE) { out->dev = cur; out->count = cur_count; return RS_OK; }   // Quantize::add_bias
+
+        // ---- sign activation: ONE batched bootstrap for every neuron of the (sliced) layer
+        if (!has_maxpool) {
+            RS_TRY(rs_pbs_batch(ctx, cur, cur, cur_count, kUnit));
+            out->dev = cur; out->count = cur_count;
+            return RS_OK;
+        }
+        PoolPlan* plan = nullptr;
+        RS_TRY(maxpool_plan(cl, &plan));
+        uint32_t* tree = nullptr;
+        RS_TRY(alloc(plan->buf_count, &tree));
+        RS_TRY(rs_pbs_batch(ctx, tree, cur, cur_count, kEighth));      // sign bits at +-1/8 for the OR gates
+        uint32_t* scratch = cur;                                        // reuse as gate pre-combination buffer
+        for (auto& st : plan->steps) {
+            if (st->csr.rows > cur_count) return RS_ERR_STATE;
+            RS_TRY(st->csr.apply(scratch, tree));
+            RS_TRY(rs_pbs_batch(ctx, tree + st->dst_offset * RS_LWE_STRIDE, scratch, st->csr.rows, st->mu));
+        }
+        uint32_t* pooled = nullptr;
+        RS_TRY(alloc(plan->out_count, &pooled));
+        RS_TRY(plan->final_gather.apply(pooled, tree));
+        rs_lwe_free(ctx, tree);
+        rs_lwe_free(ctx, scratch);
+        out->dev = pooled; out->count = plan->out_count;
+        return RS_OK;
+    }
+
+    size_t bootstraps(int cl) {
+        if (eq != E_ACTIVATION_SIGN) return 0;
+        size_t n = (size_t)q_h * q_w * cl;
+        if (has_maxpool) {
+            PoolPlan* plan = nullptr;
+            if (maxpool_plan(cl, &plan) == RS_OK) n += plan->gates;
+        }
+        return n;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- Layer
+Layer::Layer(rs_ctx* ctx, bool int_inputs, eConvType ec, uint16_t depth, ePoolType ep, eQuantType eq, tNetParams* np)
+    : impl_(new LayerImpl()) {
+    assert(np != nullptr && ec < NUM_CONVS && ep < NUM_POOLS && eq < NUM_ACTIVATIONS);
+    impl_->ctx = ctx; impl_->int_inputs = int_inputs; impl_->ec = ec; impl_->depth = depth; impl_->ep = ep; impl_->eq = eq;
+    impl_->np = *np;
+    tNetParams& p = impl_->np;
+    if (p.version < 1) {   // set_version back-compat (lib/BinLayer.cpp:252-261)
+        p.conv.stride.h = p.conv.stride.w = 1;
+        p.pool.stride.h = p.pool.stride.w = 0;
+    }
+    if (ec == E_FC || ec == E_FC_FINAL) { p.conv.window.h = p.conv.window.w = 1; p.conv.same_pad = true; p.conv.stride.h = p.conv.stride.w = 1; }
+    if (p.pool.stride.h == 0) p.pool.stride.h = p.pool.window.h;   // MaxPooling ctor (lib/BinFunc.cpp:816-817)
+    if (p.pool.stride.w == 0) p.pool.stride.w = p.pool.window.w;
+    if (ep == E_MAXPOOL) assert(eq == E_ACTIVATION_SIGN);
+}
+Layer::~Layer() = default;
+
+tDimensions* Layer::prep(FILE* fd, tDimensions* dim) {
+    in_dim = *dim;
+    if (impl_->prep(fd, dim) != RS_OK) { printf("Bad Weights File. Exiting...\r\n"); return nullptr; }
+    out_dim = *dim;
+    return dim;
+}
+
+Batch Layer::execute(Batch in) {
+    Batch out;
+    int rc = impl_->forward(in, 0, impl_->channels(), &out);
+    rs_lwe_free(impl_->ctx, in.dev);   // callee frees its input, like every Func::execute of the reference
+    if (rc != RS_OK) { out.dev = nullptr; out.count = 0; }
+    return out;
+}
+
+Batch Layer::execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int* ch_end) {
+    const int C = impl_->channels();
+    int c0 = 0, c1 = C;
+    if (shard.world > 1 && C % shard.world == 0 && (impl_->has_conv)) {
+        const int per = C / shard.world;
+        c0 = shard.rank * per; c1 = c0 + per;
+    }
+    Batch out;
+    if (impl_->forward(in, c0, c1, &out) != RS_OK) { out.dev = nullptr; out.count = 0; }
+    if (ch_begin) *ch_begin = c0;
+    if (ch_end) *ch_end = c1;
+    return out;
+}
+
+size_t Layer::out_count() const { return impl_->final_h() * impl_->final_w() * (size_t)impl_->channels(); }
+int Layer::out_channels() const { return impl_->channels(); }
+size_t Layer::bootstraps() const { return impl_->bootstraps(impl_->channels()); }
+
+// ---------------------------------------------------------------------------------------------------- Net
+Layer* Net::add(bool int_layer, eConvType ec, uint16_t depth, ePoolType ep, eQuantType eq, tNetParams* np) {
+    if (int_layer) layers_.emplace_back(new IntLayer(ctx_, ec, depth, ep, eq, np));
+    else layers_.emplace_back(new BinLayer(ctx_, ec, depth, ep, eq, np));
+    return layers_.back().get();
+}
+int Net::prep(FILE* weights, tDimensions* dim) {
+    for (auto& l : layers_) if (!l->prep(weights, dim)) return RS_ERR_ARG;
+    return RS_OK;
+}
+Batch Net::run(Batch in) {
+    for (auto& l : layers_) { in = l->execute(in); if (!in.dev) break; }
+    return in;
+}
+size_t Net::bootstraps() const { size_t n = 0; for (auto& l : layers_) n += l->bootstraps(); return n; }
+
+}  // namespace redsec
+
+// ---------------------------------------------------------------------------------------------------- flat C view
+// (used by the Python harness through ctypes; a C++ caller such as nets/*/net.cu uses the classes directly)
+struct rs_net { redsec::Net net; explicit rs_net(rs_ctx* c) : net(c) {} };
+
+extern "C" {
+
+rs_net* rs_net_create(rs_ctx* ctx) { return ctx ? new rs_net(ctx) : nullptr; }
+void rs_net_destroy(rs_net* n) { delete n; }
+
+int rs_net_add_layer(rs_net* n, int int_layer, int conv_type, int out_depth, int pool_type, int quant_type, const rs_layer_params* p) {
+    if (!n || !p) return RS_ERR_ARG;
+    tNetParams np{};
+    np.conv.window = {(int16_t)p->conv_win_h, (int16_t)p->conv_win_w};
+    np.conv.stride = {(int16_t)p->conv_stride_h, (int16_t)p->conv_stride_w};
+    np.conv.same_pad = p->conv_same_pad != 0; np.conv.tern_thresh = 0.05f;
+    np.pool.window = {(int16_t)p->pool_win_h, (int16_t)p->pool_win_w};
+    np.pool.stride = {(int16_t)p->pool_stride_h, (int16_t)p->pool_stride_w};
+    np.pool.same_pad = p->pool_same_pad != 0;
+    np.bnorm = {false, 0.001f};
+    np.quant.shift_bits = (uint8_t)p->shift_bits;
+    np.e_bias = (eBiasType)p->e_bias;
+    np.version = (uint16_t)p->version;
+    n->net.add(int_layer != 0, (eConvType)conv_type, (uint16_t)out_depth, (ePoolType)pool_type, (eQuantType)quant_type, &np);
+    return RS_OK;
+}
+
+int rs_net_prep(rs_net* n, const char* weights_path, int in_h, int in_w, int in_dep) {
+    if (!n || !weights_path) return RS_ERR_ARG;
+    FILE* fd = fopen(weights_path, "rb");
+    if (!fd) return RS_ERR_ARG;
+    tDimensions dim{};
+    dim.hw = {(int16_t)in_h, (int16_t)in_w}; dim.in_dep = (uint32_t)in_dep;
+    dim.in_bits = 9; dim.out_bits = SINGLE_BIT; dim.filter_bits = SINGLE_BIT; dim.bias_bits = SINGLE_BIT;
+    dim.up_bound = 255 * 2; dim.scale = 255;   // nets/mnist/sign1024x1/net.cpp:100-105
+    int rc = n->net.prep(fd, &dim);
+    // the file must be consumed exactly (format check of SURVEY.md 5.4)
+    if (rc == RS_OK) { int c = fgetc(fd); if (c != EOF) rc = RS_ERR_ARG; }
+    fclose(fd);
+    return rc;
+}
+
+int rs_net_num_layers(const rs_net* n) { return n ? (int)const_cast<rs_net*>(n)->net.num_layers() : 0; }
+int rs_net_layer_info(rs_net* n, int i, size_t* out_count, int* channels, size_t* bootstraps, int* out_h, int* out_w) {
+    if (!n || i < 0 || (size_t)i >= n->net.num_layers()) return RS_ERR_ARG;
+    redsec::Layer* l = n->net.layer(i);
+    if (out_count) *out_count = l->out_count();
+    if (channels) *channels = l->out_channels();
+    if (bootstraps) *bootstraps = l->bootstraps();
+    if (out_h) *out_h = l->out_dim.hw.h;
+    if (out_w) *out_w = l->out_dim.hw.w;
+    return RS_OK;
+}
+
+// runs layer i on in_dev WITHOUT consuming it; caller frees *out_dev with rs_lwe_free
+int rs_net_layer_forward(rs_net* n, int i, const uint32_t* in_dev, size_t in_count, int rank, int world, uint32_t** out_dev,
+                         size_t* out_count, int* ch_begin, int* ch_end) {
+    if (!n || i < 0 || (size_t)i >= n->net.num_layers() || !in_dev || !out_dev || !out_count) return RS_ERR_ARG;
+    redsec::Batch in; in.dev = const_cast<uint32_t*>(in_dev); in.count = in_count;
+    redsec::ShardSpec sh; sh.rank = rank; sh.world = world;
+    redsec::Batch out = n->net.layer(i)->execute_shard(in, sh, ch_begin, ch_end);
+    if (!out.dev) return RS_ERR_STATE;
+    *out_dev = out.dev; *out_count = out.count;
+    return RS_OK;
+}
+
+}  // extern "C"

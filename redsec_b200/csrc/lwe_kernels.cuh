@@ -125,4 +125,89 @@ lwe_lincomb_kernel(uint32_t* __restrict__ out, int out_count, const uint32_t* __
     }
 }
 
+// ---------------------------------------------------------------- [world][pixels][c_local] -> [pixels][world*c_local]
+__global__ void lwe_interleave_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, size_t pixels, int c_local, int world) {
+    const size_t rows = pixels * (size_t)c_local * world;
+    const int x = threadIdx.x;   // uint4 lane (88 per row)
+    for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const size_t pix = row / ((size_t)c_local * world);
+        const int ch = (int)(row % ((size_t)c_local * world));
+        const int r = ch / c_local, c = ch % c_local;
+        out[row * (LWE_STRIDE / 4) + x] = in[(((size_t)r * pixels + pix) * c_local + c) * (LWE_STRIDE / 4) + x];
+    }
+}
+
+// ---------------------------------------------------------------- ternary convolution / fully-connected layer on LWE rows
+// out[(ph,pw,od)] = (0,bias[od]) + sum_{fh,fw,di} w[fh,fw,di,od] * in[(ph*st+fh-ofs, pw*st+fw-ofs, di)]
+// Index conventions follow lib/BinFunc.cpp:388-404 (input/output (h,w,c) c-fastest; filter ((fh*W+fw)*in_dep+di)*OutDepth+od).
+// INT_MODE reproduces lib/IntFunc.cpp:268,277: a zero (ternary) weight or a padded position contributes the
+// trivial sample -1/4096 instead of 0 (lib/BinFunc.cpp:265,280 contributes 0).
+// Weights are pre-packed on the host into tiles of CONV_OD_TILE output channels: wp[tile][k][CONV_OD_TILE] int8,
+// k = (fh*win_w+fw)*in_dep+di, so one 16-byte broadcast load feeds 16 accumulators.
+constexpr int CONV_OD_TILE = 16;
+constexpr int CONV_THREADS = 96;   // 88 active lanes x uint4 = 352 words
+
+struct ConvDesc {
+    int in_h, in_w, in_dep;
+    int out_h, out_w, out_dep;
+    int win_h, win_w, stride_h, stride_w, ofs_h, ofs_w;
+    int od_begin, od_end;     // channel slice computed by this launch (neuron sharding); od_begin % CONV_OD_TILE == 0
+    uint32_t unit;            // torus value of one message unit (1/4096)
+};
+
+template <bool INT_MODE>
+__global__ void __launch_bounds__(CONV_THREADS)
+lwe_conv_kernel(uint32_t* __restrict__ out,             // [out_h*out_w][od_end-od_begin][LWE_STRIDE]
+                const uint32_t* __restrict__ in,         // [in_h*in_w*in_dep][LWE_STRIDE]
+                const int8_t* __restrict__ wp,           // [ceil(out_dep/16)][K][16]
+                const uint32_t* __restrict__ bias,       // [out_dep] torus32 or nullptr
+                ConvDesc d) {
+    const int lane = threadIdx.x;
+    if (lane >= LWE_STRIDE / 4) return;
+    const int pix = blockIdx.x, ph = pix / d.out_w, pw = pix % d.out_w;
+    const int tile = d.od_begin / CONV_OD_TILE + blockIdx.y;
+    const int K = d.win_h * d.win_w * d.in_dep;
+    const int8_t* wt = wp + (size_t)tile * K * CONV_OD_TILE;
+    uint4 acc[CONV_OD_TILE];
+    int skipped[CONV_OD_TILE];
+#pragma unroll
+    for (int o = 0; o < CONV_OD_TILE; o++) { acc[o] = make_uint4(0, 0, 0, 0); skipped[o] = 0; }
+    int oob_terms = 0;
+    for (int fh = 0; fh < d.win_h; fh++) {
+        const int iy = ph * d.stride_h + fh - d.ofs_h;
+        for (int fw = 0; fw < d.win_w; fw++) {
+            const int ix = pw * d.stride_w + fw - d.ofs_w;
+            if ((unsigned)iy >= (unsigned)d.in_h || (unsigned)ix >= (unsigned)d.in_w) { oob_terms += d.in_dep; continue; }
+            const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)((iy * d.in_w + ix) * d.in_dep) * LWE_STRIDE) + lane;
+            const int8_t* wk = wt + (size_t)((fh * d.win_w + fw) * d.in_dep) * CONV_OD_TILE;
+#pragma unroll 2
+            for (int di = 0; di < d.in_dep; di++) {
+                const uint4 v = __ldg(src + (size_t)di * (LWE_STRIDE / 4));
+                const uint4 wq = __ldg(reinterpret_cast<const uint4*>(wk + (size_t)di * CONV_OD_TILE));
+                const uint32_t wwords[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+                for (int o = 0; o < CONV_OD_TILE; o++) {
+                    const int w8 = (int)(int8_t)((wwords[o >> 2] >> ((o & 3) * 8)) & 0xFF);
+                    const uint32_t w = (uint32_t)w8;
+                    acc[o].x += w * v.x; acc[o].y += w * v.y; acc[o].z += w * v.z; acc[o].w += w * v.w;
+                    if (INT_MODE) skipped[o] += (w8 == 0);
+                }
+            }
+        }
+    }
+    const int od_count = d.od_end - d.od_begin;
+#pragma unroll
+    for (int o = 0; o < CONV_OD_TILE; o++) {
+        const int od = tile * CONV_OD_TILE + o;
+        if (od >= d.od_end || od >= d.out_dep) continue;
+        uint4 r = acc[o];
+        if (lane == LWE_N / 4) {   // words 348..351: word 350 is b
+            if (bias) r.z += bias[od];
+            if (INT_MODE) r.z -= (uint32_t)(skipped[o] + oob_terms) * d.unit;
+            r.w = 0;
+        }
+        reinterpret_cast<uint4*>(out + ((size_t)pix * od_count + (od - d.od_begin)) * LWE_STRIDE)[lane] = r;
+    }
+}
+
 }  // namespace rs

@@ -1,0 +1,110 @@
+// redsec_b200/host/redsec_layers.hpp -- host-side mirror of REDsec's layer API for the encrypted GPU path.
+//
+// Same names, constructor arguments, prep/execute sequencing and ownership rules as the reference's
+// lib/GPU/{Layer,IntLayer,BinLayer}.cuh (IntLayer/BinLayer(eConvType, uint16_t, ePoolType, eQuantType, tNetParams*),
+// tDimensions* prep(FILE*, tDimensions*), execute(...), public in_dim/out_dim), but activations are
+// device-resident LWE batches (redsec::Batch) instead of arrays of individually allocated ciphertexts, and
+// every layer issues ONE batched bootstrap launch (plus the OR-tree levels of a max-pool) through the C-ABI
+// in include/redsec_b200.h.  Implementation: redsec_b200/csrc/layers.cpp (host C++ only; all device work goes
+// through rs_* calls).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <vector>
+
+#include "../../include/redsec_b200.h"
+
+// ---- enums and parameter structs: the API surface of lib/Layer.h:38-177 / lib/GPU/Layer.cuh:42-151
+enum eConvType { E_NO_CONV, E_CONV, E_FC, E_FC_FINAL, NUM_CONVS };
+enum ePoolType { E_NO_POOL, E_MAXPOOL, E_SUMPOOL, NUM_POOLS };
+enum eBiasType { E_NO_BIAS, E_BIAS, E_BNORM, NUM_BIASES };
+enum eQuantType { E_ACTIVATION_NONE, E_ACTIVATION_SIGN, E_ACTIVATION_RELU, NUM_ACTIVATIONS };
+
+#define SIZE_EMPTY 1
+#define SINGLE_BIT 1
+#define MSG_SPACE 4096
+
+struct tRectangle { int16_t h, w; };
+struct tDimensions {
+    tRectangle hw;
+    uint32_t in_dep;
+    uint8_t in_bits, out_bits, filter_bits, bias_bits;
+    uint32_t up_bound;
+    float scale;
+};
+struct tConvParams { tRectangle window; bool same_pad; float tern_thresh; tRectangle stride; };
+struct tBNormParams { bool use_scale; float eps; };
+struct tPoolParams { tRectangle window; bool same_pad; tRectangle stride; };
+struct tQParams { uint8_t shift_bits; };
+struct tNetParams {
+    tConvParams conv;
+    tPoolParams pool;
+    tBNormParams bnorm;
+    tQParams quant;
+    eBiasType e_bias;
+    uint16_t version;
+};
+
+namespace redsec {
+
+// A batch of LWE ciphertexts on the device (rows of RS_LWE_STRIDE words).  Ownership follows the reference:
+// every execute() consumes (frees) its input and returns a freshly allocated batch (lib/BinFunc.cpp:327-329,1073).
+struct Batch {
+    uint32_t* dev = nullptr;
+    size_t count = 0;
+};
+
+struct ShardSpec {   // neuron sharding across ranks: contiguous blocks of output channels
+    int rank = 0, world = 1;
+};
+
+class LayerImpl;
+
+// Common implementation; IntLayer / BinLayer below differ only in the conv semantics for zero weights and padding
+// (lib/IntFunc.cpp:268,277 vs lib/BinFunc.cpp:265,280).
+class Layer {
+public:
+    Layer(rs_ctx* ctx, bool int_inputs, eConvType ec, uint16_t depth, ePoolType ep, eQuantType eq, tNetParams* np);
+    ~Layer();
+    tDimensions* prep(FILE* fd, tDimensions* dim);       // lib/BinLayer.cpp:89-113, lib/IntLayer.cpp:93-117
+    Batch execute(Batch in);                              // lib/BinLayer.cpp:122-127 (run(E_EXEC))
+    // Sharded execution: computes this rank's output-channel slice [begin,end) of the layer for all pixels,
+    // bootstraps and max-pools it locally; the caller all-gathers the slices (rows [pixel][c_local]) and
+    // calls interleave_shards() to restore the canonical (h,w,c) order.
+    Batch execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int* ch_end);
+    size_t out_count() const;                             // ciphertexts in the full output
+    int out_channels() const;
+    size_t bootstraps() const;                            // PBS issued per execute (sign + OR tree)
+    tDimensions in_dim{}, out_dim{};
+private:
+    std::unique_ptr<LayerImpl> impl_;
+};
+
+class IntLayer : public Layer {   // lib/GPU/IntLayer.cuh:16-34
+public:
+    IntLayer(rs_ctx* ctx, eConvType ec, uint16_t depth, ePoolType ep, eQuantType eq, tNetParams* np)
+        : Layer(ctx, true, ec, depth, ep, eq, np) {}
+};
+class BinLayer : public Layer {   // lib/GPU/BinLayer.cuh:16-34
+public:
+    BinLayer(rs_ctx* ctx, eConvType ec, uint16_t depth, ePoolType ep, eQuantType eq, tNetParams* np)
+        : Layer(ctx, false, ec, depth, ep, eq, np) {}
+};
+
+// A sequential network = the generated HeBNN classes of nets/*/net.cu (init + run).
+class Net {
+public:
+    explicit Net(rs_ctx* ctx) : ctx_(ctx) {}
+    Layer* add(bool int_layer, eConvType ec, uint16_t depth, ePoolType ep, eQuantType eq, tNetParams* np);
+    int prep(FILE* weights, tDimensions* input_dim);      // HeBNN::init (nets/mnist/sign1024x1/net.cpp:46-113)
+    Batch run(Batch in);                                  // HeBNN::run (net.cpp:117-131); consumes in
+    size_t num_layers() const { return layers_.size(); }
+    Layer* layer(size_t i) { return layers_[i].get(); }
+    size_t bootstraps() const;
+private:
+    rs_ctx* ctx_;
+    std::vector<std::unique_ptr<Layer>> layers_;
+};
+
+}  // namespace redsec

@@ -1,0 +1,111 @@
+"""Python harness around the C++ Layer/Net classes (redsec_b200/csrc/layers.cpp) for tests and bench.py.
+
+Mirrors HeBNN::init / HeBNN::run of nets/*/net.cu: build the layer list from a spec (redsec_b200/netspec.py),
+prep() reads var_prep.dat, run() executes layer by layer with activations resident on the device.  With
+torch.distributed initialised (world > 1) every shardable layer computes only this rank's output-channel block
+and the slices are all-gathered over NCCL between layers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .engine import LWE_STRIDE, Engine, LweArray, RsError
+from .netspec import ACT, CONV, POOL
+
+
+class LayerParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "conv_win_h", "conv_win_w", "conv_stride_h", "conv_stride_w", "conv_same_pad",
+        "pool_win_h", "pool_win_w", "pool_stride_h", "pool_stride_w", "pool_same_pad",
+        "e_bias", "shift_bits", "version")]
+
+
+class EncryptedNet:
+    def __init__(self, eng: Engine, spec: dict):
+        self.eng, self.spec, self.lib = eng, spec, eng.lib
+        self.net = self.lib.rs_net_create(eng.ctx)
+        if not self.net:
+            raise RsError("rs_net_create failed")
+        for ls in spec["layers"]:
+            p = LayerParams(ls["conv_win"][0], ls["conv_win"][1], ls["conv_stride"][0], ls["conv_stride"][1], int(ls["conv_same_pad"]),
+                            ls["pool_win"][0], ls["pool_win"][1], ls["pool_stride"][0], ls["pool_stride"][1], int(ls["pool_same_pad"]),
+                            ls["e_bias"], 1, ls["version"])
+            eng._chk(self.lib.rs_net_add_layer(self.net, int(ls["kind"] == "int"), CONV[ls["conv"]], ls["depth"], POOL[ls["pool"]],
+                                               ACT[ls["act"]], C.byref(p)))
+        h, w, c = spec["input"]
+        rc = self.lib.rs_net_prep(self.net, spec["weights"].encode(), h, w, c)
+        if rc != 0:
+            raise RsError(f"rs_net_prep({spec['weights']}) failed with code {rc} (bad or mismatching weight file)")
+        self.num_layers = self.lib.rs_net_num_layers(self.net)
+
+    def close(self):
+        if self.net:
+            self.lib.rs_net_destroy(self.net)
+            self.net = None
+
+    def layer_info(self, i: int) -> dict:
+        oc, ch, bs, oh, ow = C.c_size_t(), C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
+        self.eng._chk(self.lib.rs_net_layer_info(self.net, i, C.byref(oc), C.byref(ch), C.byref(bs), C.byref(oh), C.byref(ow)))
+        return dict(out_count=oc.value, channels=ch.value, bootstraps=bs.value, out_h=oh.value, out_w=ow.value)
+
+    def bootstraps(self) -> int:
+        return sum(self.layer_info(i)["bootstraps"] for i in range(self.num_layers))
+
+    def layer_forward(self, i: int, inp: LweArray, rank: int = 0, world: int = 1):
+        """One layer for this rank's channel slice; returns (LweArray rows [pixel][c_local], c0, c1)."""
+        out, cnt, c0, c1 = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
+        self.eng._chk(self.lib.rs_net_layer_forward(self.net, i, inp.ptr, inp.count, rank, world, C.byref(out), C.byref(cnt),
+                                                    C.byref(c0), C.byref(c1)))
+        arr = LweArray(self.eng, cnt.value, out.value)
+        arr._owned = True     # allocated with rs_lwe_alloc inside the library; freed through rs_lwe_free
+        return arr, c0.value, c1.value
+
+    def run(self, inp: LweArray, collect: list | None = None, dist=None) -> LweArray:
+        """HeBNN::run.  dist = (torch.distributed module, rank, world) enables neuron sharding + all-gather."""
+        x = inp
+        for i in range(self.num_layers):
+            if dist is None or dist[2] == 1:
+                y, _, _ = self.layer_forward(i, x)
+            else:
+                y = self._layer_sharded(i, x, dist)
+            if collect is not None:
+                collect.append(self.eng.download(y))
+            if x is not inp:
+                x.free()
+            x = y
+        return x
+
+    def _layer_sharded(self, i: int, x: LweArray, dist) -> LweArray:
+        import torch
+        td, rank, world = dist
+        info = self.layer_info(i)
+        y, c0, c1 = self.layer_forward(i, x, rank, world)
+        if c1 - c0 == info["channels"]:
+            return y                                   # layer not shardable: computed replicated on every rank
+        self.eng.sync()
+        dev = torch.device("cuda", self.eng.device)
+        words = y.count * LWE_STRIDE
+        local = _as_tensor(y.ptr, words, dev)
+        gathered = torch.empty(world * words, dtype=torch.int32, device=dev)
+        td.all_gather_into_tensor(gathered, local)     # NCCL over NVLink: the exchange step between layers
+        torch.cuda.current_stream(dev).synchronize()
+        out = self.eng.alloc(world * y.count)
+        pixels = y.count // (c1 - c0)
+        self.eng._chk(self.lib.rs_lwe_interleave(self.eng.ctx, out.ptr, gathered.data_ptr(), pixels, c1 - c0, world))
+        self.eng.sync()
+        y.free()
+        return out
+
+
+def _as_tensor(ptr: int, words: int, dev):
+    """Zero-copy torch view of library-owned device memory (for torch.distributed collectives)."""
+    import torch
+
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device=dev)

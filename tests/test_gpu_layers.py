@@ -1,0 +1,120 @@
+"""GPU parity of Layer forward against the CPU oracle on the same keyset and the same
+input ciphertexts: every layer output is compared ciphertext-for-ciphertext (bit-exact), and the decrypted
+class scores are checked against the reference's plaintext scores."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from redsec_b200 import netspec
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ptxt_scores.json")))
+
+
+def _nets():
+    from redsec_b200 import nets
+    return nets
+
+
+def test_lincomb_kernel_bit_exact(oracle, engine):
+    rng = np.random.default_rng(3)
+    inp = rng.integers(0, 2 ** 32, size=(50, 351), dtype=np.uint64).astype(np.uint32)
+    rowptr, col, sign = [0], [], []
+    for o in range(37):
+        k = int(rng.integers(0, 9))
+        col += list(rng.integers(0, 50, k)); sign += list(rng.choice([-1, 1, 2, -3], k))
+        rowptr.append(len(col))
+    bias = rng.integers(0, 2 ** 32, 37, dtype=np.uint64).astype(np.uint32)
+    want = oracle.lincomb(inp, rowptr, col, sign, bias)
+    d_in = engine.upload(inp)
+    out = engine.alloc(37)
+    ptrs = [engine.dev_upload(np.asarray(a, dtype=t)) for a, t in ((rowptr, np.int32), (col, np.int32), (sign, np.int8), (bias, np.uint32))]
+    engine.lincomb(out, d_in, *ptrs)
+    got = engine.download(out)
+    for p in ptrs:
+        engine.dev_free(p)
+    assert np.array_equal(got, want)
+
+
+def test_mnist_sign1024x1_layers_bit_exact_and_scores(oracle, keyset, engine):
+    from oracle import layers_oracle as LO
+    nets = _nets()
+    spec = netspec.NETS["mnist/sign1024x1"]()
+    label, px = netspec.load_image_csv(spec["image"])
+    ct = oracle.encrypt(LO.encode_pixels(px), 2.0 ** -15, keyset.lwe_key, 42)
+    layers = LO.prepare(spec, spec["weights"])
+    want = []
+    LO.enc_forward(layers, ct, keyset, collect=want)
+    net = nets.EncryptedNet(engine, spec)
+    assert net.bootstraps() == 1220
+    got = []
+    out = net.run(engine.upload(ct), collect=got)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w), f"layer {i} ciphertexts differ"
+    scores = oracle.decrypt(engine.download(out), keyset.lwe_key, 4096)
+    gold = GOLD["mnist/sign1024x1|client/mnist_test.csv|1"][0]["scores"]
+    assert int(np.argmax(scores)) == int(np.argmax(gold)) == label
+    # encrypted scores follow the plaintext ones up to threshold flips of near-zero neurons
+    assert np.max(np.abs(scores - np.asarray(gold))) < 120
+    net.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_tiny_conv_maxpool_net_bit_exact_and_sharding(oracle, keyset, engine, tmp_path, world):
+    from oracle import layers_oracle as LO
+    nets = _nets()
+    spec = netspec.tiny_cifar_like()
+    spec["weights"] = netspec.write_random_weights(spec, str(tmp_path / "w.dat"), seed=5, p_zero=0.2, bias_range=3)
+    rng = np.random.default_rng(8)
+    px = rng.integers(0, 256, 8 * 8 * 3)
+    ct = oracle.encrypt(LO.encode_pixels(px), 2.0 ** -15, keyset.lwe_key, 43)
+    layers = LO.prepare(spec, spec["weights"])
+    want = []
+    LO.enc_forward(layers, ct, keyset, collect=want)
+    net = nets.EncryptedNet(engine, spec)
+    assert net.bootstraps() == LO.count_bootstraps(layers)
+    got = []
+    net.run(engine.upload(ct), collect=got)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w), f"layer {i} ciphertexts differ"
+    # neuron sharding emulated on one GPU: per-rank channel slices, concatenated as an all-gather would, interleaved back
+    x = engine.upload(ct)
+    for i in range(net.num_layers):
+        info = net.layer_info(i)
+        parts, slices = [], []
+        for r in range(world):
+            y, c0, c1 = net.layer_forward(i, x, r, world)
+            parts.append(y); slices.append((c0, c1))
+        if slices[0] == (0, info["channels"]):
+            full = parts[0]
+        else:
+            cl = slices[0][1] - slices[0][0]
+            cat = engine.upload(np.concatenate([engine.download(p) for p in parts]))
+            full = engine.alloc(cat.count)
+            engine._chk(engine.lib.rs_lwe_interleave(engine.ctx, full.ptr, cat.ptr, parts[0].count // cl, cl, world))
+        assert np.array_equal(engine.download(full), want[i]), f"sharded layer {i} (world {world})"
+        x = full
+    net.close()
+
+
+def test_builder_cnn_int_conv_bit_exact(oracle, keyset, engine):
+    """Config 4 (builder-defined MNIST CNN): integer conv with the -1/4096 zero/padding convention + sum-pool."""
+    from oracle import layers_oracle as LO
+    nets = _nets()
+    spec = netspec.NETS["mnist/cnn_builder"]()
+    label, px = netspec.load_image_csv(spec["image"])
+    x5 = 2 * (np.asarray(px) >> 3) - 31                 # 5-bit inputs
+    ct = oracle.encrypt((x5.astype(np.int64) << 20) & 0xFFFFFFFF, 2.0 ** -15, keyset.lwe_key, 44)
+    layers = LO.prepare(spec, spec["weights"])
+    # the full CNN is 4832 bootstraps; compare the linear parts of the first two layers exactly and the rest on the GPU path
+    net = nets.EncryptedNet(engine, spec)
+    assert net.bootstraps() == 4832
+    d = engine.upload(ct)
+    y0, _, _ = net.layer_forward(0, d)
+    assert np.array_equal(engine.download(y0), LO.enc_layer_forward(layers[0], ct, keyset))
+    want1 = LO.enc_layer_forward(layers[1], engine.download(y0), keyset)
+    y1, _, _ = net.layer_forward(1, y0)
+    assert np.array_equal(engine.download(y1), want1)
+    net.close()
