@@ -150,6 +150,8 @@ typedef struct rs_layer_params {    /* tNetParams, lib/Layer.h:126-167 */
     int32_t pool_win_h, pool_win_w, pool_stride_h, pool_stride_w, pool_same_pad;
     int32_t e_bias, shift_bits, version;
 } rs_layer_params;
+/* neuron partition of one layer: output-channel block [ch_begin,ch_end) of `rank`; whole layer when not shardable */
+int rs_shard_range(int channels, int has_conv, int rank, int world, int *ch_begin, int *ch_end);
 rs_net *rs_net_create(rs_ctx *ctx);
 void rs_net_destroy(rs_net *net);
 int rs_net_add_layer(rs_net *net, int int_layer, int conv_type, int out_depth, int pool_type, int quant_type,

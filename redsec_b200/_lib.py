@@ -54,6 +54,7 @@ SIGNATURES = {
     "rs_read_eval_key": (C.c_int, [C.c_char_p, vp, vp]),
     "rs_write_ctxt": (C.c_int, [C.c_char_p, vp, C.c_size_t, C.c_double, C.c_int]),
     "rs_read_ctxt": (C.c_int, [C.c_char_p, vp, C.c_size_t]),
+    "rs_shard_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rs_net_create": (vp, [vp]),
     "rs_net_destroy": (None, [vp]),
     "rs_net_add_layer": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

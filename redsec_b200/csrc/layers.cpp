@@ -477,12 +477,8 @@ Batch Layer::execute(Batch in) {
 }
 
 Batch Layer::execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int* ch_end) {
-    const int C = impl_->channels();
-    int c0 = 0, c1 = C;
-    if (shard.world > 1 && C % shard.world == 0 && (impl_->has_conv)) {
-        const int per = C / shard.world;
-        c0 = shard.rank * per; c1 = c0 + per;
-    }
+    int c0 = 0, c1 = impl_->channels();
+    rs_shard_range(impl_->channels(), impl_->has_conv ? 1 : 0, shard.rank, shard.world, &c0, &c1);
     Batch out;
     if (impl_->forward(in, c0, c1, &out) != RS_OK) { out.dev = nullptr; out.count = 0; }
     if (ch_begin) *ch_begin = c0;
@@ -517,6 +513,18 @@ size_t Net::bootstraps() const { size_t n = 0; for (auto& l : layers_) n += l->b
 struct rs_net { redsec::Net net; explicit rs_net(rs_ctx* c) : net(c) {} };
 
 extern "C" {
+
+// Neuron partition: contiguous blocks of output channels; a layer is sharded only when it has a
+// conv/FC stage and its channel count divides evenly, otherwise every rank computes it whole (replicated).
+int rs_shard_range(int channels, int has_conv, int rank, int world, int* ch_begin, int* ch_end) {
+    if (!ch_begin || !ch_end || channels <= 0 || world <= 0 || rank < 0 || rank >= world) return RS_ERR_ARG;
+    *ch_begin = 0; *ch_end = channels;
+    if (world > 1 && has_conv && channels % world == 0) {
+        const int per = channels / world;
+        *ch_begin = rank * per; *ch_end = *ch_begin + per;
+    }
+    return RS_OK;
+}
 
 rs_net* rs_net_create(rs_ctx* ctx) { return ctx ? new rs_net(ctx) : nullptr; }
 void rs_net_destroy(rs_net* n) { delete n; }

@@ -100,6 +100,22 @@ class EncryptedNet:
         return out
 
 
+def shard_range(channels: int, has_conv: bool, rank: int, world: int):
+    """rs_shard_range: the output-channel block a rank computes (usable without a GPU)."""
+    lib = _lib.load()
+    c0, c1 = C.c_int(), C.c_int()
+    rc = lib.rs_shard_range(channels, int(has_conv), rank, world, C.byref(c0), C.byref(c1))
+    if rc != 0:
+        raise RsError(f"rs_shard_range failed with code {rc}")
+    return c0.value, c1.value
+
+
+def interleave_index(pixels: int, c_local: int, world: int) -> np.ndarray:
+    """Row permutation applied by rs_lwe_interleave: out row (pix, r*c_local+c) <- gathered row (r, pix, c)."""
+    pix, r, c = np.meshgrid(np.arange(pixels), np.arange(world), np.arange(c_local), indexing="ij")
+    return ((r * pixels + pix) * c_local + c).reshape(-1)
+
+
 def _as_tensor(ptr: int, words: int, dev):
     """Zero-copy torch view of library-owned device memory (for torch.distributed collectives)."""
     import torch
