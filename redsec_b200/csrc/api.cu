@@ -48,7 +48,7 @@ struct rs_ctx {
     double prof_ms[RS_K_COUNT] = {0, 0, 0, 0};
     uint64_t prof_n[RS_K_COUNT] = {0, 0, 0, 0};
     uint64_t launches = 0;
-    int br_groups = 4;
+    int br_variant = 0;
 };
 
 namespace {
@@ -97,7 +97,8 @@ int grow(rs_ctx* ctx, uint32_t** p, size_t* cap, size_t words) {
 }
 
 // Blind-rotation variants: (ciphertext groups per CTA, BSK ring stages).  4 groups = 8 warps = 2 per SM
-// sub-partition (255 registers/thread, no spills); 6 groups = 12 warps = 3 per sub-partition (168 registers).
+// sub-partition (255 registers/thread).  More groups would put 3 warps on a sub-partition (168 registers/thread,
+// which spills).  Variant 0 = 7-stage BSK ring (default), variant 1 = 4-stage ring.
 struct BrVariant { int groups, stages, smem; void (*set_attr)(cudaError_t*); };
 template <int G, int S>
 void br_launch(rs_ctx* ctx, int grid, const uint32_t* in, int count, uint32_t mu, uint32_t* ext) {
@@ -107,17 +108,17 @@ template <int G, int S>
 cudaError_t br_prepare() {
     return cudaFuncSetAttribute(rs::blind_rotate_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::BrSmem<G, S>::kTotal);
 }
-constexpr int kMaxSmemNeeded = rs::BrSmem<6, 4>::kTotal;
+constexpr int kMaxSmemNeeded = rs::BrSmem<4, 7>::kTotal;
 
 int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t count, uint32_t mu) {
     if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
     if (count == 0) return RS_OK;
-    const int G = ctx->br_groups;
+    constexpr int G = 4;
     const int grid = (int)((count + G - 1) / G);
     {
         LaunchScope ls(ctx, RS_K_BLIND_ROTATE);
-        if (G == 4) br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext);
-        else br_launch<6, 4>(ctx, grid, in, (int)count, mu, ext);
+        if (ctx->br_variant == 0) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext);
+        else br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext);
     }
     RS_CUDA(ctx, cudaGetLastError());
     return RS_OK;
@@ -177,10 +178,10 @@ int rs_ctx_create(rs_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    e = br_prepare<4, 4>();
-    if (e == cudaSuccess) e = br_prepare<6, 4>();
+    e = br_prepare<4, 7>();
+    if (e == cudaSuccess) e = br_prepare<4, 4>();
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
-    if (const char* env = getenv("RS_BR_GROUPS")) { int g = atoi(env); if (g == 4 || g == 6) ctx->br_groups = g; }
+    if (const char* env = getenv("RS_BR_VARIANT")) { int v = atoi(env); if (v == 0 || v == 1) ctx->br_variant = v; }
     *out = ctx;
     return RS_OK;
 }
@@ -505,9 +506,29 @@ int rs_fp64_peak(rs_ctx* ctx, double* tflops) {
     return RS_OK;
 }
 
-int rs_set_tuning(rs_ctx* ctx, int br_groups) {
-    if (!ctx || (br_groups != 4 && br_groups != 6)) return fail(ctx, RS_ERR_ARG, "rs_set_tuning: br_groups must be 4 or 6");
-    ctx->br_groups = br_groups;
+#ifdef RS_BR_STATS
+int* rs_debug_progress() {   // host-mapped progress words of block 0 (debug builds only)
+    static int* host = nullptr;
+    if (!host) {
+        cudaHostAlloc(&host, 64 * sizeof(int), cudaHostAllocMapped);
+        memset(host, 0xff, 64 * sizeof(int));
+        int* dev = nullptr;
+        cudaHostGetDevicePointer(&dev, host, 0);
+        cudaMemcpyToSymbol(rs::g_br_progress, &dev, sizeof(dev));
+    }
+    return host;
+}
+int rs_debug_stats(unsigned long long* out8, int reset) {
+    cudaDeviceSynchronize();
+    if (out8) cudaMemcpyFromSymbol(out8, rs::g_br_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(rs::g_br_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
+int rs_set_tuning(rs_ctx* ctx, int br_variant) {
+    if (!ctx || (br_variant != 0 && br_variant != 1)) return fail(ctx, RS_ERR_ARG, "rs_set_tuning: br_variant must be 0 or 1");
+    ctx->br_variant = br_variant;
     return RS_OK;
 }
 

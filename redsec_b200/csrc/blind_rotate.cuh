@@ -4,13 +4,15 @@
 // time through redcufhe::Bootstrap (lib/GPU/gates.cu:124-130) / tfhe_bootstrap_FFT (lib/BinOps_enc.cpp:185):
 //   modswitch to 2N  ->  acc = X^{-b} * testvector(mu)  ->  for i<n: acc += BK_i (x) ((X^{a_i}-1) acc)
 //   -> sample-extract coefficient 0.
-// Layout per CTA: GROUPS independent 64-thread groups (one ciphertext each).  Thread 0 of group 0 is
-// also the producer: it streams the Fourier-domain bootstrapping key, one 16 KiB (i,row) slab at a time,
-// with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a STAGES-deep shared-memory
-// ring; all groups of the CTA consume the same slab (full/empty mbarrier pipeline), so each BSK byte is
-// fetched once per CTA per step and reused GROUPS times.  (A dedicated producer warp would be the 4k+1-th
-// warp of the CTA and push one SM sub-partition to an extra resident warp, which cuts the register
-// budget of every thread from 255/168 to 168/128; hence the in-line producer.)
+// Layout per CTA: GROUPS independent 64-thread groups (one ciphertext each).  The Fourier-domain bootstrapping key
+// is streamed one 16 KiB (i,row) slab at a time with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx)
+// into a STAGES-deep shared-memory ring; all groups of the CTA consume the same slab (full/empty mbarrier pipeline),
+// so each BSK byte is fetched once per CTA per step and reused GROUPS times.  There is no fixed producer: the first
+// group to start row rc claims (CAS on a shared counter) and requests every slab up to rc+AHEAD, so the group that
+// runs ahead feeds the ring, followers find their slabs already resident, and the leader is throttled only by the
+// ring depth.  (A fixed producer thread paces the CTA: measured, the other three groups spent 27 % of their time
+// waiting for slabs it had not requested yet.  A dedicated producer warp would be the 4k+1-th warp of the CTA and
+// push one SM sub-partition to an extra resident warp, which cuts the register budget of every thread.)
 #pragma once
 #include "fft512.cuh"
 #include "params.h"
@@ -19,44 +21,84 @@ namespace rs {
 
 // ---------------------------------------------------------------- mbarrier / TMA helpers (inline PTX)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// mbarriers are addressed by their 32-bit shared-space address, computed once per kernel
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {    // may suspend for a bounded time
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
 }
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// Spin on an mbarrier phase.  A wait that lasts longer than ~2 s is a protocol bug: trap, so that a mistake shows up
+// as a failed launch instead of a hung GPU.
+// mbar_wait_thread: for code that ONE thread of a warp executes (inside an `if (lane == ...)` region).
+__device__ __forceinline__ void mbar_wait_thread(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+// mbar_wait_warp: executed by all 32 lanes of a converged warp.  Every lane polls (its own successful try_wait is its
+// acquire of the TMA-written data) but the loop exit is decided by a vote, so the warp leaves the loop CONVERGED.
+// A per-lane exit is not just slower: lanes of one warp can see the phase flip on different polls, the compiler puts no
+// reconvergence point after such a loop, and the warp-uniform loop counters that follow (uniform datapath) were then
+// advanced once per divergent subset -- observed as one warp of a group skipping a row and a hang at the last barrier.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    if (__all_sync(0xffffffffu, mbar_try(bar, parity))) return;
+    const long long t0 = clock64();
+    while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking phase test
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+#ifdef RS_BR_STATS
+__device__ volatile int* g_br_progress;        // host-mapped: [group][4] = {row, site, aux, _} of block 0
+#define RS_PROGRESS(site, aux) do { if (blockIdx.x == 0 && (threadIdx.x & 31) < 2 && g_br_progress) { volatile int* q_ = g_br_progress + ((threadIdx.x >> 5) * 2 + (threadIdx.x & 31)) * 4; q_[0] = rc; q_[1] = (site); q_[2] = (aux); } } while (0)
+__device__ unsigned long long g_br_stats[8];   // [0] warp-cycles total, [1] cycles in full-wait, [2] first-test failures, [3] waits
+#endif
+#ifndef RS_BR_STATS
+#define RS_PROGRESS(site, aux) do { } while (0)
+#endif
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
 
 // ---------------------------------------------------------------- shared-memory plan
 template <int GROUPS, int STAGES>
-struct BrSmem {
+struct BrSmem {   // STAGES = depth of the BSK slab ring
     static constexpr int kStageBytes = (int)BSK_ROW_BYTES;                   // 16 KiB
     static constexpr int kAccBytes = 2 * N * 4;                              // 8 KiB: a-poly, b-poly (torus32)
-    static constexpr int kBuf1Bytes = FFT_BUF1 * 16;
-    static constexpr int kBuf2Bytes = FFT_BUF2 * 16;
+    static constexpr int kBufBytes = FFT_BUF * 16;                           // one exchange buffer, 8 KiB
     static constexpr int kBaraBytes = 352 * 2;
-    static constexpr int kGroupBytes = kAccBytes + kBuf1Bytes + kBuf2Bytes + kBaraBytes;   // 26,304 B
+    static constexpr int kGroupBytes = kAccBytes + 2 * kBufBytes + kBaraBytes;   // 25,280 B
     static constexpr int kStagesOff = 0;
     static constexpr int kGroupsOff = STAGES * kStageBytes;
     static constexpr int kBarOff = kGroupsOff + GROUPS * kGroupBytes;
-    static constexpr int kTotal = kBarOff + 2 * STAGES * 8;
+    static constexpr int kIssuedOff = kBarOff + 2 * STAGES * 8;     // int: number of slabs requested so far
+    static constexpr int kTotal = kIssuedOff + 8;
 };
 
 __device__ __forceinline__ uint32_t modswitch_2N(uint32_t x) {   // modSwitchFromTorus32(x, 2N) mod 2N
@@ -78,9 +120,12 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
                     uint32_t* __restrict__ ext_out)          // [count][EXT_STRIDE]
 {
     using S = BrSmem<GROUPS, STAGES>;
+    constexpr int AHEAD = 2;                // a group starting row rc makes sure slabs <= rc+AHEAD have been requested
+    static_assert(STAGES > AHEAD + 1, "ring too shallow");
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
-    uint64_t* empty_bar = full_bar + STAGES;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + S::kBarOff;        // full[STAGES] then empty[STAGES], 8 bytes each
+    int* issued = reinterpret_cast<int*>(smem + S::kIssuedOff);
 
     const int first_ct = blockIdx.x * GROUPS;
     const int active = min(GROUPS, count - first_ct);
@@ -88,22 +133,17 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], active * 64);
+            mbar_init(bar_base + s * 8, 1);
+            mbar_init(bar_base + (STAGES + s) * 8, active * 2);     // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *issued = 0;
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5;
-    const bool producer = threadIdx.x == 0;
+    const int lane = threadIdx.x & 31;
     const uint8_t* bsk_bytes = reinterpret_cast<const uint8_t*>(bsk_f);
-    if (producer) {   // prologue: fill STAGES-1 slots
-        for (int r = 0; r < STAGES - 1; r++) {
-            mbar_arrive_expect_tx(&full_bar[r], S::kStageBytes);
-            tma_load_1d(smem + S::kStagesOff + r * S::kStageBytes, bsk_bytes + (size_t)r * S::kStageBytes, S::kStageBytes, &full_bar[r]);
-        }
-    }
     const int g = warp >> 1;
     if (g >= active) return;
     const int t = threadIdx.x & 63;
@@ -111,9 +151,8 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
 
     uint8_t* gbase = smem + S::kGroupsOff + g * S::kGroupBytes;
     uint32_t* acc = reinterpret_cast<uint32_t*>(gbase);
-    double2* buf1 = reinterpret_cast<double2*>(gbase + S::kAccBytes);
-    double2* buf2 = reinterpret_cast<double2*>(gbase + S::kAccBytes + S::kBuf1Bytes);
-    uint16_t* bara = reinterpret_cast<uint16_t*>(gbase + S::kAccBytes + S::kBuf1Bytes + S::kBuf2Bytes);
+    double2* xbuf = reinterpret_cast<double2*>(gbase + S::kAccBytes);          // two exchange buffers, used alternately
+    uint16_t* bara = reinterpret_cast<uint16_t*>(gbase + S::kAccBytes + 2 * S::kBufBytes);
 
     // ---- modswitch and accumulator init (step 2)
     const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
@@ -123,11 +162,15 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
         acc[j] = 0;
         acc[N + j] = (((j + barb) & (2 * N - 1)) < N) ? mu : 0u - mu;   // X^{2N-barb} * (mu + mu X + ...)
     }
-    TwiddlesT<(GROUPS > 4)> tw;
+    Twiddles tw;
     make_twiddles(tw, t);
     group_sync(g);
 
-    int rc = 0;   // BSK slab counter (same sequence in every group and in the producer)
+#ifdef RS_BR_STATS
+    long long st_wait = 0, st_t0 = clock64(); unsigned st_fail = 0, st_n = 0;
+#endif
+    int rc = 0;     // BSK slab counter (same sequence in every group and in the producer)
+    int par = 0;    // which exchange buffer the next transform uses
 #pragma unroll 1
     for (int i = 0; i < LWE_N; i++) {
         const int a = bara[i];
@@ -145,16 +188,31 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
             }
 #pragma unroll 1
             for (int p = 0; p < BK_L; p++) {
-                if (producer) {   // refill the slot released by slab rc-1 with slab rc+STAGES-1
-                    const int nr = rc + STAGES - 1;
-                    if (nr < kTotalRows) {
-                        const int ns = nr % STAGES;
-                        if (rc > 0) mbar_wait(&empty_bar[ns], ((rc - 1) / STAGES) & 1);
-                        mbar_arrive_expect_tx(&full_bar[ns], S::kStageBytes);
-                        tma_load_1d(smem + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)nr * S::kStageBytes,
-                                    S::kStageBytes, &full_bar[ns]);
+                // BSK producer duty, taken by whichever group gets here first: slabs are claimed in order with a CAS on
+                // `issued`, so the group that runs ahead feeds the ring and no group paces the others.  A claimed slab
+                // first waits for its ring slot (slab n-STAGES released by every consumer warp), so the leader can be at
+                // most STAGES-AHEAD-1 rows ahead of the slowest group.
+                RS_PROGRESS(1, 0);
+                if (t == 0) {
+                    const int want = min(rc + AHEAD, kTotalRows - 1);
+                    int cur = *reinterpret_cast<volatile int*>(issued);
+                    while (cur <= want) {
+                        const int prev = atomicCAS(issued, cur, cur + 1);
+                        if (prev == cur) {
+                            const int ns = cur % STAGES;
+                            RS_PROGRESS(2, cur);
+                            if (cur >= STAGES) mbar_wait_thread(bar_base + (STAGES + ns) * 8, ((cur - STAGES) / STAGES) & 1);
+                            mbar_arrive_expect_tx(bar_base + ns * 8, S::kStageBytes);
+                            tma_load_1d(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
+                                        S::kStageBytes, bar_base + ns * 8);
+                            cur++;
+                        } else {
+                            cur = prev;
+                        }
                     }
                 }
+                __syncwarp();
+                RS_PROGRESS(3, 0);
                 const int sh = 32 - (p + 1) * BK_BGBIT;
                 double2 v[8];
 #pragma unroll
@@ -162,32 +220,52 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
                     v[q].x = (double)((int)((src[2 * q] >> sh) & 7u) - 4);
                     v[q].y = (double)((int)((src[2 * q + 1] >> sh) & 7u) - 4);
                 }
-                fft512_fwd(v, tw, buf1, buf2, t, g);
-
                 const int s = rc % STAGES;
-                mbar_wait(&full_bar[s], (rc / STAGES) & 1);
-                const double2* B = reinterpret_cast<const double2*>(smem + S::kStagesOff + s * S::kStageBytes);
+                // test the slab's barrier now (non-blocking) and consume the answer after the transform: the ~100-cycle
+                // mbarrier round trip is off the critical path, and a slab requested >= AHEAD rows ago has landed.
+                const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + s * 8, (rc / STAGES) & 1));
+                fft512_fwd(v, tw, xbuf + par * FFT_BUF, t, g);
+                par ^= 1;
+#ifdef RS_BR_STATS
+                RS_PROGRESS(4, slab_ready);
+                { const long long c0 = clock64();
+                  if (!slab_ready) mbar_wait_warp(bar_base + s * 8, (rc / STAGES) & 1);
+                  st_wait += clock64() - c0; st_fail += !slab_ready; st_n++; }
+#else
+                if (!slab_ready) mbar_wait_warp(bar_base + s * 8, (rc / STAGES) & 1);
+#endif
+
+                const double2* B = reinterpret_cast<const double2*>(smem + S::kStagesOff + s * S::kStageBytes) + t;
+                double2 b0 = B[0], b1 = B[NH];
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
-                    const double2 b0 = B[x * 64 + t], b1 = B[NH + x * 64 + t];
-                    f0[x].x += v[x].x * b0.x - v[x].y * b0.y;
-                    f0[x].y += v[x].x * b0.y + v[x].y * b0.x;
-                    f1[x].x += v[x].x * b1.x - v[x].y * b1.y;
-                    f1[x].y += v[x].x * b1.y + v[x].y * b1.x;
+                    double2 n0, n1;
+                    if (x < 7) { n0 = B[(x + 1) * 64]; n1 = B[NH + (x + 1) * 64]; }
+                    f0[x].x = fma(-v[x].y, b0.y, fma(v[x].x, b0.x, f0[x].x));
+                    f0[x].y = fma(v[x].y, b0.x, fma(v[x].x, b0.y, f0[x].y));
+                    f1[x].x = fma(-v[x].y, b1.y, fma(v[x].x, b1.x, f1[x].x));
+                    f1[x].y = fma(v[x].y, b1.x, fma(v[x].x, b1.y, f1[x].y));
+                    if (x < 7) { b0 = n0; b1 = n1; }
                 }
-                mbar_arrive(&empty_bar[s]);
+                RS_PROGRESS(5, 0);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + (STAGES + s) * 8);
+                RS_PROGRESS(6, *reinterpret_cast<volatile int*>(issued));
                 rc++;
             }
         }
-        group_sync(g);   // last forward exchange reads finished before the inverse reuses buf2
-        // ---- inverse transforms, round to nearest, accumulate into acc (exact integers mod 2^32)
-        fft512_inv(f0, tw, buf1, buf2, t, g);
+        RS_PROGRESS(7, i);
+        // ---- inverse transforms, round to nearest, accumulate into acc (exact integers mod 2^32).
+        // acc was last read (rot_diff) before the 20 barriers of the forward transforms, so it can be updated in place.
+        fft512_inv(f0, tw, xbuf + par * FFT_BUF, t, g);
+        par ^= 1;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             acc[t + 64 * q] += (uint32_t)__double2ll_rn(f0[q].x);
             acc[t + 64 * q + NH] += (uint32_t)__double2ll_rn(f0[q].y);
         }
-        fft512_inv(f1, tw, buf1, buf2, t, g);
+        fft512_inv(f1, tw, xbuf + par * FFT_BUF, t, g);
+        par ^= 1;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             acc[N + t + 64 * q] += (uint32_t)__double2ll_rn(f1[q].x);
@@ -196,6 +274,15 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
         group_sync(g);
     }
 
+#ifdef RS_BR_STATS
+    if (lane == 0) {
+        atomicAdd(&g_br_stats[0], (unsigned long long)(clock64() - st_t0));
+        atomicAdd(&g_br_stats[1], (unsigned long long)st_wait);
+        atomicAdd(&g_br_stats[2], (unsigned long long)st_fail);
+        atomicAdd(&g_br_stats[3], (unsigned long long)st_n);
+        atomicAdd(&g_br_stats[4 + (g & 3)], (unsigned long long)st_fail);
+    }
+#endif
     // ---- sample extract: a'[0]=acc_a[0], a'[j]=-acc_a[N-j], b'=acc_b[0]
     uint32_t* ext = ext_out + (size_t)ct * EXT_STRIDE;
     for (int j = t; j < N; j += 64) ext[j] = (j == 0) ? acc[0] : 0u - acc[N - j];
@@ -203,24 +290,25 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
 }
 
 // ---------------------------------------------------------------- BSK -> Fourier-domain device layout (north-star item (c))
-// One 64-thread group per polynomial; same forward routine as the blind rotation, so the slot layout matches.
+// One 64-thread group per polynomial; same forward routine as the blind rotation (so the slot layout matches by
+// construction) followed by the phase factor that routine leaves out (fft512.cuh header).
 __global__ void __launch_bounds__(64)
 bsk_to_fourier_kernel(const int32_t* __restrict__ bsk, double2* __restrict__ bsk_f, int npolys) {
-    __shared__ double2 buf1[FFT_BUF1];
-    __shared__ double2 buf2[FFT_BUF2];
+    __shared__ double2 buf[2 * FFT_BUF];
     const int t = threadIdx.x;
     Twiddles tw;
     make_twiddles(tw, t);
+    int par = 0;
     for (int poly = blockIdx.x; poly < npolys; poly += gridDim.x) {
         const int32_t* p = bsk + (size_t)poly * N;
         double2 v[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) v[q] = make_double2((double)p[t + 64 * q], (double)p[t + 64 * q + NH]);
-        fft512_fwd(v, tw, buf1, buf2, t, 0);
+        fft512_fwd(v, tw, buf + par * FFT_BUF, t, 0);
+        par ^= 1;
         double2* o = bsk_f + (size_t)poly * NH;
 #pragma unroll
-        for (int x = 0; x < 8; x++) o[x * 64 + t] = v[x];
-        __syncthreads();
+        for (int x = 0; x < 8; x++) o[x * 64 + t] = cmul(v[x], fwd_phase(t, x));
     }
 }
 

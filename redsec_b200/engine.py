@@ -189,8 +189,8 @@ class Engine:
         self._chk(self.lib.rs_fp64_peak(self.ctx, C.byref(v)))
         return v.value
 
-    def set_tuning(self, br_groups: int):
-        self._chk(self.lib.rs_set_tuning(self.ctx, br_groups))
+    def set_tuning(self, br_variant: int):
+        self._chk(self.lib.rs_set_tuning(self.ctx, br_variant))
 
     def device_info(self):
         sm, ma, mi, sh = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()

@@ -46,14 +46,14 @@ def test_pbs_bit_exact_and_decrypts(oracle, keyset, engine, count):
     assert np.array_equal(dec, np.where(bits == 1, 1, -1))
 
 
-@pytest.mark.parametrize("groups", [4, 6])
+@pytest.mark.parametrize("groups", [0, 1])
 def test_variants_agree(oracle, keyset, engine, groups):
     bits, ct = _rand_bits_ct(oracle, keyset, 29, MU8, 2.0 ** -25, 77)
     engine.set_tuning(groups)
     try:
         got = engine.download(engine.pbs(engine.upload(ct), MU8))
     finally:
-        engine.set_tuning(4)
+        engine.set_tuning(0)
     assert np.array_equal(got, oracle.pbs(ct, MU8, keyset))
 
 
