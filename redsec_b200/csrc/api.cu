@@ -12,6 +12,7 @@
 
 #include "../../include/redsec_b200.h"
 #include "blind_rotate.cuh"
+#include "blind_rotate_ws.cuh"
 #include "lwe_kernels.cuh"
 #include "params.h"
 
@@ -98,7 +99,8 @@ int grow(rs_ctx* ctx, uint32_t** p, size_t* cap, size_t words) {
 
 // Blind-rotation variants: (ciphertext groups per CTA, BSK ring stages).  4 groups = 8 warps = 2 per SM
 // sub-partition (255 registers/thread).  More groups would put 3 warps on a sub-partition (168 registers/thread,
-// which spills).  Variant 0 = 7-stage BSK ring (default), variant 1 = 4-stage ring.
+// which spills).  Variant 0 (default) = warp-specialised kernel (blind_rotate_ws.cuh: 12 warps, front/back roles,
+// setmaxnreg); variant 1 = single-role kernel with a 7-stage BSK ring; variant 2 = same with a 4-stage ring.
 struct BrVariant { int groups, stages, smem; void (*set_attr)(cudaError_t*); };
 template <int G, int S>
 void br_launch(rs_ctx* ctx, int grid, const uint32_t* in, int count, uint32_t mu, uint32_t* ext) {
@@ -108,7 +110,9 @@ template <int G, int S>
 cudaError_t br_prepare() {
     return cudaFuncSetAttribute(rs::blind_rotate_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::BrSmem<G, S>::kTotal);
 }
-constexpr int kMaxSmemNeeded = rs::BrSmem<4, 7>::kTotal;
+constexpr int kWsStages = 5, kWsSlots = 3;
+constexpr int kMaxSmemNeeded = rs::BrSmem<4, 7>::kTotal > rs::WsSmem<kWsStages, kWsSlots>::kTotal ? rs::BrSmem<4, 7>::kTotal
+                                                                                            : rs::WsSmem<kWsStages, kWsSlots>::kTotal;
 
 int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t count, uint32_t mu) {
     if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
@@ -117,7 +121,10 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
     const int grid = (int)((count + G - 1) / G);
     {
         LaunchScope ls(ctx, RS_K_BLIND_ROTATE);
-        if (ctx->br_variant == 0) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext);
+        if (ctx->br_variant == 0)
+            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots><<<grid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
+                in, (int)count, mu, ctx->bsk_f, ext);
+        else if (ctx->br_variant == 1) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext);
         else br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext);
     }
     RS_CUDA(ctx, cudaGetLastError());
@@ -178,10 +185,12 @@ int rs_ctx_create(rs_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    e = br_prepare<4, 7>();
+    e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             rs::WsSmem<kWsStages, kWsSlots>::kTotal);
+    if (e == cudaSuccess) e = br_prepare<4, 7>();
     if (e == cudaSuccess) e = br_prepare<4, 4>();
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
-    if (const char* env = getenv("RS_BR_VARIANT")) { int v = atoi(env); if (v == 0 || v == 1) ctx->br_variant = v; }
+    if (const char* env = getenv("RS_BR_VARIANT")) { int v = atoi(env); if (v >= 0 && v <= 2) ctx->br_variant = v; }
     *out = ctx;
     return RS_OK;
 }
@@ -527,7 +536,7 @@ int rs_debug_stats(unsigned long long* out8, int reset) {
 #endif
 
 int rs_set_tuning(rs_ctx* ctx, int br_variant) {
-    if (!ctx || (br_variant != 0 && br_variant != 1)) return fail(ctx, RS_ERR_ARG, "rs_set_tuning: br_variant must be 0 or 1");
+    if (!ctx || br_variant < 0 || br_variant > 2) return fail(ctx, RS_ERR_ARG, "rs_set_tuning: br_variant must be 0, 1 or 2");
     ctx->br_variant = br_variant;
     return RS_OK;
 }

@@ -1,0 +1,294 @@
+// redsec_b200/csrc/blind_rotate_ws.cuh -- warp-specialised batched blind rotation + sample extract for sm_100a.
+//
+// Same computation as blind_rotate.cuh (the role of tfhe_bootstrap_FFT at lib/BinOps_enc.cpp:185 /
+// redcufhe::Bootstrap at lib/GPU/gates.cu:124-130 for a whole batch), re-cut as a three-stage pipeline so that every SM
+// sub-partition has THREE resident warps with different phases instead of two in near lock-step:
+//
+//   TMA (cp.async.bulk)  --BSK ring-->  BACK warps  <--exchange ring--  FRONT warps
+//
+// One CTA = 12 warps = 3 warpgroups, 4 ciphertexts:
+//   * warpgroup 2 = 4 FRONT warps, one per ciphertext.  A front warp owns the torus32 accumulator (shared memory): per
+//     blind-rotate step it forms (X^a - 1)*acc, gadget-decomposes it, and for each of the 20 (polynomial, level) rows
+//     runs pass 1 of the forward transform (twist + radix-8) for all 64 thread-columns (two halves of 32) and writes the
+//     result into a 3-slot exchange ring.  After the 20 rows it finishes the two inverse transforms (last radix-8 pass,
+//     untwist, round to nearest) and adds them into the accumulator.  It also claims and requests BSK slabs (TMA).
+//   * warpgroups 0,1 = 8 BACK warps, two per ciphertext.  A back warp reads a row from the exchange ring, runs passes 2
+//     and 3 (twiddles fused as FMAs, exchange 2 through shuffles), multiplies by the BSK slab and accumulates in
+//     registers (Fourier accumulators, 64 registers).  After 20 rows it runs the first two passes of both inverse
+//     transforms and hands them to the front warp through ring slots 0 and 1.
+//   The two back warps of a ciphertext never synchronise with each other during the 20 rows (exchange 1 is now
+//   front -> back, exchange 2 is intra-warp); all hand-offs are mbarriers, so the roles drift freely within the rings.
+//   * Registers are redistributed with setmaxnreg: launch at 168/thread (12 warps), front warps drop to 120, back warps
+//     grow to 192.  The pool is what the launch allocated (384*168 = 64512 registers, not the 65536 of the SM):
+//     8*32*192 + 4*32*120 = 64512.  (Asking for more blocks setmaxnreg.inc forever.)
+//
+// See fft512.cuh for the transform algebra; the arithmetic per row is identical to blind_rotate_kernel, so results are
+// bit-identical (tests/test_gpu_pbs.py::test_variants_agree).
+#pragma once
+#include "blind_rotate.cuh"
+
+namespace rs {
+
+template <int STAGES, int XSLOTS>
+struct WsSmem {
+    static constexpr int kCts = 4;
+    static constexpr int kStageBytes = (int)BSK_ROW_BYTES;                 // 16 KiB BSK slab
+    static constexpr int kAccBytes = 2 * N * 4;                            // 8 KiB
+    static constexpr int kBaraBytes = 352 * 2;
+    static constexpr int kSlotBytes = FFT_BUF * 16;                        // 8 KiB exchange slot
+    static constexpr int kCtBytes = kAccBytes + kBaraBytes + XSLOTS * kSlotBytes;
+    static constexpr int kStagesOff = 0;
+    static constexpr int kCtOff = STAGES * kStageBytes;
+    static constexpr int kBarOff = kCtOff + kCts * kCtBytes;
+    // barriers (8 B each): bsk_full[STAGES], bsk_empty[STAGES], x_full[4][XSLOTS], x_empty[4][XSLOTS], inv_full[4][2]
+    static constexpr int kBskFull = 0, kBskEmpty = STAGES, kXFull = 2 * STAGES, kXEmpty = kXFull + kCts * XSLOTS,
+                         kInvFull = kXEmpty + kCts * XSLOTS, kNumBars = kInvFull + kCts * 2;
+    static constexpr int kIssuedOff = kBarOff + kNumBars * 8;
+    static constexpr int kTotal = kIssuedOff + 8;
+    static_assert(kCtBytes % 16 == 0, "ciphertext block must stay 16-byte aligned");
+    static_assert(XSLOTS >= 2, "inverse hand-off uses slots 0 and 1");
+};
+
+template <int N_REGS>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N_REGS)); }
+template <int N_REGS>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N_REGS)); }
+
+// digit in [0,8) (decomposition digit + 4) -> (double)(digit - 4) without the XU pipe: 2^52 + 2^31 + m is exactly
+// representable with low word 0x80000000 + m; one DADD removes the offset.
+__device__ __forceinline__ double digit_to_double(uint32_t biased_digit) {
+    return __hiloint2double(0x43300000, (int)(0x7FFFFFFCu + biased_digit)) - 4503601774854144.0;
+}
+
+template <int STAGES, int XSLOTS>
+__global__ void __launch_bounds__(384, 1)
+blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRIDE]
+                       int count, uint32_t mu,
+                       const double2* __restrict__ bsk_f,       // [n][BK_ROWS][2][NH]
+                       uint32_t* __restrict__ ext_out)          // [count][EXT_STRIDE]
+{
+    using S = WsSmem<STAGES, XSLOTS>;
+    constexpr int AHEAD = 1;                       // a front warp starting row r makes sure slabs <= r+AHEAD are requested
+    constexpr int kTotalRows = LWE_N * BK_ROWS;
+    static_assert(STAGES > AHEAD + XSLOTS, "BSK ring must cover the front-to-back distance");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + S::kBarOff;
+    int* issued = reinterpret_cast<int*>(smem + S::kIssuedOff);
+
+    const int first_ct = blockIdx.x * S::kCts;
+    const int active = min(S::kCts, count - first_ct);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(bar_base + (S::kBskFull + s) * 8, 1);
+            mbar_init(bar_base + (S::kBskEmpty + s) * 8, active * 2);      // one arrival per back warp
+        }
+        for (int j = 0; j < S::kCts; j++) {
+            for (int x = 0; x < XSLOTS; x++) {
+                mbar_init(bar_base + (S::kXFull + j * XSLOTS + x) * 8, 1);   // the front warp
+                mbar_init(bar_base + (S::kXEmpty + j * XSLOTS + x) * 8, 2);  // the two back warps
+            }
+            mbar_init(bar_base + (S::kInvFull + j * 2 + 0) * 8, 2);
+            mbar_init(bar_base + (S::kInvFull + j * 2 + 1) * 8, 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *issued = 0;
+    }
+    __syncthreads();
+
+    if (warp >= 8) {
+        // =========================================================================================== FRONT warp
+        reg_dealloc<120>();
+        const int j = warp - 8;
+        if (j >= active) return;
+        const int ct = first_ct + j;
+        uint8_t* cbase = smem + S::kCtOff + j * S::kCtBytes;
+        uint32_t* acc = reinterpret_cast<uint32_t*>(cbase);
+        uint16_t* bara = reinterpret_cast<uint16_t*>(cbase + S::kAccBytes);
+        double2* ring = reinterpret_cast<double2*>(cbase + S::kAccBytes + S::kBaraBytes);
+        const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
+        const uint32_t invfull = bar_base + (S::kInvFull + j * 2) * 8;
+        const uint8_t* bsk_bytes = reinterpret_cast<const uint8_t*>(bsk_f);
+
+        // ---- modswitch and accumulator init (step 2)
+        const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
+        for (int i = lane; i < LWE_N; i += 32) bara[i] = (uint16_t)modswitch_2N(lwe[i]);
+        const int barb = (int)modswitch_2N(lwe[LWE_N]);
+        for (int k = lane; k < N; k += 32) {
+            acc[k] = 0;
+            acc[N + k] = (((k + barb) & (2 * N - 1)) < N) ? mu : 0u - mu;   // X^{2N-barb} * (mu + mu X + ...)
+        }
+        __syncwarp();
+
+        int rowc = 0;    // rows produced by this front warp (= BSK slab index of the row)
+#pragma unroll 1
+        for (int i = 0; i < LWE_N; i++) {
+            const int a = bara[i];
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                uint32_t src[2][16];   // (X^a - 1)*acc_c + decomposition offset at this lane's 2 x 16 coefficients
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        src[hf][2 * q] = rot_diff(acc + c * N, lane + 32 * hf + 64 * q, a) + DECOMP_OFFSET;
+                        src[hf][2 * q + 1] = rot_diff(acc + c * N, lane + 32 * hf + 64 * q + NH, a) + DECOMP_OFFSET;
+                    }
+                }
+#pragma unroll 1
+                for (int p = 0; p < BK_L; p++) {
+                    // ---- BSK producer duty (claimed in order by whichever front warp gets here first)
+                    if (lane == 0) {
+                        const int want = min(rowc + AHEAD, kTotalRows - 1);
+                        int cur = *reinterpret_cast<volatile int*>(issued);
+                        while (cur <= want) {
+                            const int prev = atomicCAS(issued, cur, cur + 1);
+                            if (prev == cur) {
+                                const int ns = cur % STAGES;
+                                if (cur >= STAGES)
+                                    mbar_wait_thread(bar_base + (S::kBskEmpty + ns) * 8, ((cur - STAGES) / STAGES) & 1);
+                                mbar_arrive_expect_tx(bar_base + (S::kBskFull + ns) * 8, S::kStageBytes);
+                                tma_load_1d(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
+                                            S::kStageBytes, bar_base + (S::kBskFull + ns) * 8);
+                                cur++;
+                            } else {
+                                cur = prev;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // ---- ring slot: wait until both back warps have read its previous occupant
+                    const int slot = rowc % XSLOTS;
+                    if (rowc >= XSLOTS) mbar_wait_warp(xempty + slot * 8, ((rowc - XSLOTS) / XSLOTS) & 1);
+                    double2* buf = ring + slot * FFT_BUF;
+                    const int sh = 32 - (p + 1) * BK_BGBIT;
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        double2 v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            v[q].x = digit_to_double((src[hf][2 * q] >> sh) & 7u);
+                            v[q].y = digit_to_double((src[hf][2 * q + 1] >> sh) & 7u);
+                        }
+                        dft8_twiddled<-1, true>(v, [](int q) { return twist_const(q); });
+#pragma unroll
+                        for (int r = 0; r < 8; r++) buf[r * 64 + lane + 32 * hf] = v[r];
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(xfull + slot * 8);
+                    rowc++;
+                }
+            }
+            // ---- finish the two inverse transforms (last radix-8 pass, untwist, scale), round, accumulate
+#pragma unroll 1
+            for (int poly = 0; poly < 2; poly++) {
+                mbar_wait_warp(invfull + poly * 8, i & 1);
+                const double2* buf = ring + poly * FFT_BUF;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; hf++) {
+                    const int t = lane + 32 * hf;
+                    double2 v[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) v[r] = buf[r * 64 + t];
+                    dft8<+1>(v);
+                    v[0] = make_double2(v[0].x * (1.0 / 512.0), v[0].y * (1.0 / 512.0));
+#pragma unroll
+                    for (int q = 1; q < 8; q++) {
+                        double2 w = twist_const(q);
+                        w.x *= (1.0 / 512.0); w.y *= (1.0 / 512.0);
+                        v[q] = cmul_conj(v[q], w);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        acc[poly * N + t + 64 * q] += (uint32_t)__double2ll_rn(v[q].x);
+                        acc[poly * N + t + 64 * q + NH] += (uint32_t)__double2ll_rn(v[q].y);
+                    }
+                }
+            }
+            __syncwarp();   // accumulator updates of all lanes are visible before the next step's rot_diff
+        }
+        // ---- sample extract: a'[0]=acc_a[0], a'[k]=-acc_a[N-k], b'=acc_b[0]
+        uint32_t* ext = ext_out + (size_t)ct * EXT_STRIDE;
+        for (int k = lane; k < N; k += 32) ext[k] = (k == 0) ? acc[0] : 0u - acc[N - k];
+        if (lane == 0) { ext[N] = acc[N]; ext[N + 1] = 0; ext[N + 2] = 0; ext[N + 3] = 0; }
+        return;
+    }
+
+    // =============================================================================================== BACK warp
+    reg_alloc<192>();
+    const int j = warp >> 1;
+    if (j >= active) return;
+    const int u = lane + 32 * (warp & 1);      // thread-column of the 64-wide transform layout
+    const int lo = u & 7, rr = u >> 3;
+    uint8_t* cbase = smem + S::kCtOff + j * S::kCtBytes;
+    double2* ring = reinterpret_cast<double2*>(cbase + S::kAccBytes + S::kBaraBytes);
+    const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
+    const uint32_t invfull = bar_base + (S::kInvFull + j * 2) * 8;
+    Twiddles tw;
+    make_twiddles(tw, u);
+
+    int rowc = 0;
+#pragma unroll 1
+    for (int i = 0; i < LWE_N; i++) {
+        double2 f0[8], f1[8];   // Fourier accumulators for the two output polynomials
+#pragma unroll
+        for (int x = 0; x < 8; x++) { f0[x] = make_double2(0.0, 0.0); f1[x] = make_double2(0.0, 0.0); }
+#pragma unroll 1
+        for (int row = 0; row < 2 * BK_L; row++) {
+            const int slot = rowc % XSLOTS;
+            const int s = rowc % STAGES;
+            // test the slab's barrier now and consume the answer after the transform (mbarrier round trip off the critical path)
+            const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1));
+            mbar_wait_warp(xfull + slot * 8, (rowc / XSLOTS) & 1);
+            const double2* buf = ring + slot * FFT_BUF;
+            double2 v[8];
+#pragma unroll
+            for (int q2 = 0; q2 < 8; q2++) v[q2] = buf[rr * 64 + lo + 8 * q2];
+            dft8_twiddled<-1, false>(v, [&](int q) { return tw.g[q]; });
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xempty + slot * 8);      // the row has been consumed into registers
+            rotate_exchange(v, lo);
+            dft8_twiddled<+1, false>(v, [&](int k) { return tw.h[k]; });
+
+            if (!slab_ready) mbar_wait_warp(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1);
+            const double2* B = reinterpret_cast<const double2*>(smem + S::kStagesOff + s * S::kStageBytes) + u;
+            double2 b0 = B[0], b1 = B[NH];
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                double2 n0, n1;
+                if (x < 7) { n0 = B[(x + 1) * 64]; n1 = B[NH + (x + 1) * 64]; }
+                f0[x].x = fma(-v[x].y, b0.y, fma(v[x].x, b0.x, f0[x].x));
+                f0[x].y = fma(v[x].y, b0.x, fma(v[x].x, b0.y, f0[x].y));
+                f1[x].x = fma(-v[x].y, b1.y, fma(v[x].x, b1.x, f1[x].x));
+                f1[x].y = fma(v[x].y, b1.x, fma(v[x].x, b1.y, f1[x].y));
+                if (x < 7) { b0 = n0; b1 = n1; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_base + (S::kBskEmpty + s) * 8);
+            rowc++;
+        }
+        // ---- first two passes of the inverse transforms; hand the result to the front warp through ring slots 0, 1.
+        // Both back warps must be done reading the step's forward rows before either overwrites a slot.
+        group_sync(j);
+        auto inverse_handoff = [&](double2 (&f)[8], int poly) {
+            dft8<+1>(f);
+            f[0] = cmul_conj(f[0], tw.h[0]);
+#pragma unroll
+            for (int k = 1; k < 8; k++) f[k] = cmul_conj(f[k], tw.h[8 - k]);
+            rotate_exchange(f, lo);
+            dft8<-1>(f);
+            double2* buf = ring + poly * FFT_BUF;
+#pragma unroll
+            for (int q2 = 0; q2 < 8; q2++) buf[rr * 64 + lo + 8 * q2] = cmul_conj(f[q2], tw.g[q2]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(invfull + poly * 8);
+        };
+        inverse_handoff(f0, 0);
+        inverse_handoff(f1, 1);
+    }
+}
+
+}  // namespace rs
