@@ -63,6 +63,25 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+__device__ __forceinline__ uint32_t mbar_try_hint(uint32_t bar, uint32_t parity, uint32_t ns) {   // suspend up to ~ns
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok;
+}
+// as mbar_wait_warp, for waits that are expected to last (pipeline hand-offs): polls with a suspend-time hint so that
+// the waiting warp does not burn issue slots its neighbours need.
+__device__ __forceinline__ void mbar_wait_warp_long(uint32_t bar, uint32_t parity) {
+    if (__all_sync(0xffffffffu, mbar_try(bar, parity))) return;
+    const long long t0 = clock64();
+    while (!__all_sync(0xffffffffu, mbar_try_hint(bar, parity, 2000u))) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
 __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking phase test
     uint32_t ok;
     asm volatile(
@@ -103,6 +122,29 @@ struct BrSmem {   // STAGES = depth of the BSK slab ring
 
 __device__ __forceinline__ uint32_t modswitch_2N(uint32_t x) {   // modSwitchFromTorus32(x, 2N) mod 2N
     return ((x + (1u << 20)) >> 21) & (2 * N - 1);
+}
+
+// Gadget digit -> double without shifts or the XU pipe.  src already carries the decomposition offset, so level p's
+// digit+4 sits in bits [sh, sh+3) with sh = 29-3p.  Masking those bits into the low word of 2^52 gives the exact double
+// 2^52 + (digit+4)*2^sh; one DADD removes 2^52 + 4*2^sh and leaves (digit)*2^sh.  The power-of-two scale is undone for
+// free: row (c,p) of the Fourier BSK is stored multiplied by 2^-sh (bsk_to_fourier_kernel), which is exact.
+struct DigitLevel {
+    uint32_t mask;   // 7 << sh
+    double bias;     // 2^52 + 4 * 2^sh
+};
+__device__ __forceinline__ DigitLevel digit_level(int p) {
+    const int sh = 32 - (p + 1) * BK_BGBIT;
+    DigitLevel d;
+    d.mask = 7u << sh;
+    d.bias = __hiloint2double(0x43300000, (int)(4u << sh));
+    return d;
+}
+__device__ __forceinline__ double digit_scaled(uint32_t src, const DigitLevel& d) {
+    return __hiloint2double(0x43300000, (int)(src & d.mask)) - d.bias;
+}
+__device__ __forceinline__ double bsk_row_scale(int row) {   // 2^-sh of gadget level p = row % l
+    const int sh = 32 - ((row % BK_L) + 1) * BK_BGBIT;
+    return __hiloint2double((1023 - sh) << 20, 0);
 }
 
 // coefficient j of (X^a - 1) * poly, a in [0, 2N)
@@ -213,12 +255,12 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
                 }
                 __syncwarp();
                 RS_PROGRESS(3, 0);
-                const int sh = 32 - (p + 1) * BK_BGBIT;
+                const DigitLevel dl = digit_level(p);
                 double2 v[8];
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
-                    v[q].x = (double)((int)((src[2 * q] >> sh) & 7u) - 4);
-                    v[q].y = (double)((int)((src[2 * q + 1] >> sh) & 7u) - 4);
+                    v[q].x = digit_scaled(src[2 * q], dl);
+                    v[q].y = digit_scaled(src[2 * q + 1], dl);
                 }
                 const int s = rc % STAGES;
                 // test the slab's barrier now (non-blocking) and consume the answer after the transform: the ~100-cycle
@@ -291,7 +333,8 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
 
 // ---------------------------------------------------------------- BSK -> Fourier-domain device layout (north-star item (c))
 // One 64-thread group per polynomial; same forward routine as the blind rotation (so the slot layout matches by
-// construction) followed by the phase factor that routine leaves out (fft512.cuh header).
+// construction) followed by the phase factor that routine leaves out (fft512.cuh header) and the power-of-two row
+// scale that pays for the shift-free digit extraction (digit_scaled above).
 __global__ void __launch_bounds__(64)
 bsk_to_fourier_kernel(const int32_t* __restrict__ bsk, double2* __restrict__ bsk_f, int npolys) {
     __shared__ double2 buf[2 * FFT_BUF];
@@ -307,8 +350,12 @@ bsk_to_fourier_kernel(const int32_t* __restrict__ bsk, double2* __restrict__ bsk
         fft512_fwd(v, tw, buf + par * FFT_BUF, t, 0);
         par ^= 1;
         double2* o = bsk_f + (size_t)poly * NH;
+        const double sc = bsk_row_scale((poly >> 1) % BK_ROWS);     // poly = ((i*BK_ROWS + row)*2 + out)
 #pragma unroll
-        for (int x = 0; x < 8; x++) o[x * 64 + t] = cmul(v[x], fwd_phase(t, x));
+        for (int x = 0; x < 8; x++) {
+            const double2 w = cmul(v[x], fwd_phase(t, x));
+            o[x * 64 + t] = make_double2(w.x * sc, w.y * sc);
+        }
     }
 }
 

@@ -10,12 +10,12 @@
 //   * warpgroup 2 = 4 FRONT warps, one per ciphertext.  A front warp owns the torus32 accumulator (shared memory): per
 //     blind-rotate step it forms (X^a - 1)*acc, gadget-decomposes it, and for each of the 20 (polynomial, level) rows
 //     runs pass 1 of the forward transform (twist + radix-8) for all 64 thread-columns (two halves of 32) and writes the
-//     result into a 3-slot exchange ring.  After the 20 rows it finishes the two inverse transforms (last radix-8 pass,
-//     untwist, round to nearest) and adds them into the accumulator.  It also claims and requests BSK slabs (TMA).
+//     result into a 3-slot exchange ring.  It also claims and requests BSK slabs (TMA).  It is the lighter role on
+//     purpose: the ring stays full and the back warps, which carry the FP64 bulk, never wait for it.
 //   * warpgroups 0,1 = 8 BACK warps, two per ciphertext.  A back warp reads a row from the exchange ring, runs passes 2
 //     and 3 (twiddles fused as FMAs, exchange 2 through shuffles), multiplies by the BSK slab and accumulates in
-//     registers (Fourier accumulators, 64 registers).  After 20 rows it runs the first two passes of both inverse
-//     transforms and hands them to the front warp through ring slots 0 and 1.
+//     registers (Fourier accumulators, 64 registers).  After 20 rows the pair runs both inverse transforms (their
+//     exchange 1 goes through the idle ring slots 0 and 1), rounds, adds into the accumulator and signals acc_ready.
 //   The two back warps of a ciphertext never synchronise with each other during the 20 rows (exchange 1 is now
 //   front -> back, exchange 2 is intra-warp); all hand-offs are mbarriers, so the roles drift freely within the rings.
 //   * Registers are redistributed with setmaxnreg: launch at 168/thread (12 warps), front warps drop to 120, back warps
@@ -40,9 +40,9 @@ struct WsSmem {
     static constexpr int kStagesOff = 0;
     static constexpr int kCtOff = STAGES * kStageBytes;
     static constexpr int kBarOff = kCtOff + kCts * kCtBytes;
-    // barriers (8 B each): bsk_full[STAGES], bsk_empty[STAGES], x_full[4][XSLOTS], x_empty[4][XSLOTS], inv_full[4][2]
+    // barriers (8 B each): bsk_full[STAGES], bsk_empty[STAGES], x_full[4][XSLOTS], x_empty[4][XSLOTS], acc_ready[4]
     static constexpr int kBskFull = 0, kBskEmpty = STAGES, kXFull = 2 * STAGES, kXEmpty = kXFull + kCts * XSLOTS,
-                         kInvFull = kXEmpty + kCts * XSLOTS, kNumBars = kInvFull + kCts * 2;
+                         kAccReady = kXEmpty + kCts * XSLOTS, kNumBars = kAccReady + kCts;
     static constexpr int kIssuedOff = kBarOff + kNumBars * 8;
     static constexpr int kTotal = kIssuedOff + 8;
     static_assert(kCtBytes % 16 == 0, "ciphertext block must stay 16-byte aligned");
@@ -53,12 +53,6 @@ template <int N_REGS>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N_REGS)); }
 template <int N_REGS>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N_REGS)); }
-
-// digit in [0,8) (decomposition digit + 4) -> (double)(digit - 4) without the XU pipe: 2^52 + 2^31 + m is exactly
-// representable with low word 0x80000000 + m; one DADD removes the offset.
-__device__ __forceinline__ double digit_to_double(uint32_t biased_digit) {
-    return __hiloint2double(0x43300000, (int)(0x7FFFFFFCu + biased_digit)) - 4503601774854144.0;
-}
 
 template <int STAGES, int XSLOTS>
 __global__ void __launch_bounds__(384, 1)
@@ -91,8 +85,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 mbar_init(bar_base + (S::kXFull + j * XSLOTS + x) * 8, 1);   // the front warp
                 mbar_init(bar_base + (S::kXEmpty + j * XSLOTS + x) * 8, 2);  // the two back warps
             }
-            mbar_init(bar_base + (S::kInvFull + j * 2 + 0) * 8, 2);
-            mbar_init(bar_base + (S::kInvFull + j * 2 + 1) * 8, 2);
+            mbar_init(bar_base + (S::kAccReady + j) * 8, 2);               // the two back warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *issued = 0;
@@ -110,7 +103,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         uint16_t* bara = reinterpret_cast<uint16_t*>(cbase + S::kAccBytes);
         double2* ring = reinterpret_cast<double2*>(cbase + S::kAccBytes + S::kBaraBytes);
         const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
-        const uint32_t invfull = bar_base + (S::kInvFull + j * 2) * 8;
+        const uint32_t accready = bar_base + (S::kAccReady + j) * 8;
         const uint8_t* bsk_bytes = reinterpret_cast<const uint8_t*>(bsk_f);
 
         // ---- modswitch and accumulator init (step 2)
@@ -126,6 +119,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         int rowc = 0;    // rows produced by this front warp (= BSK slab index of the row)
 #pragma unroll 1
         for (int i = 0; i < LWE_N; i++) {
+            if (i > 0) mbar_wait_warp_long(accready, (i - 1) & 1);   // back warps have added step i-1 into the accumulator
             const int a = bara[i];
 #pragma unroll 1
             for (int c = 0; c < 2; c++) {
@@ -164,14 +158,14 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                     const int slot = rowc % XSLOTS;
                     if (rowc >= XSLOTS) mbar_wait_warp(xempty + slot * 8, ((rowc - XSLOTS) / XSLOTS) & 1);
                     double2* buf = ring + slot * FFT_BUF;
-                    const int sh = 32 - (p + 1) * BK_BGBIT;
+                    const DigitLevel dl = digit_level(p);
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++) {
                         double2 v[8];
 #pragma unroll
                         for (int q = 0; q < 8; q++) {
-                            v[q].x = digit_to_double((src[hf][2 * q] >> sh) & 7u);
-                            v[q].y = digit_to_double((src[hf][2 * q + 1] >> sh) & 7u);
+                            v[q].x = digit_scaled(src[hf][2 * q], dl);
+                            v[q].y = digit_scaled(src[hf][2 * q + 1], dl);
                         }
                         dft8_twiddled<-1, true>(v, [](int q) { return twist_const(q); });
 #pragma unroll
@@ -182,34 +176,8 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                     rowc++;
                 }
             }
-            // ---- finish the two inverse transforms (last radix-8 pass, untwist, scale), round, accumulate
-#pragma unroll 1
-            for (int poly = 0; poly < 2; poly++) {
-                mbar_wait_warp(invfull + poly * 8, i & 1);
-                const double2* buf = ring + poly * FFT_BUF;
-#pragma unroll 1
-                for (int hf = 0; hf < 2; hf++) {
-                    const int t = lane + 32 * hf;
-                    double2 v[8];
-#pragma unroll
-                    for (int r = 0; r < 8; r++) v[r] = buf[r * 64 + t];
-                    dft8<+1>(v);
-                    v[0] = make_double2(v[0].x * (1.0 / 512.0), v[0].y * (1.0 / 512.0));
-#pragma unroll
-                    for (int q = 1; q < 8; q++) {
-                        double2 w = twist_const(q);
-                        w.x *= (1.0 / 512.0); w.y *= (1.0 / 512.0);
-                        v[q] = cmul_conj(v[q], w);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        acc[poly * N + t + 64 * q] += (uint32_t)__double2ll_rn(v[q].x);
-                        acc[poly * N + t + 64 * q + NH] += (uint32_t)__double2ll_rn(v[q].y);
-                    }
-                }
-            }
-            __syncwarp();   // accumulator updates of all lanes are visible before the next step's rot_diff
         }
+        mbar_wait_warp_long(accready, (LWE_N - 1) & 1);     // the last step's accumulator update
         // ---- sample extract: a'[0]=acc_a[0], a'[k]=-acc_a[N-k], b'=acc_b[0]
         uint32_t* ext = ext_out + (size_t)ct * EXT_STRIDE;
         for (int k = lane; k < N; k += 32) ext[k] = (k == 0) ? acc[0] : 0u - acc[N - k];
@@ -226,7 +194,8 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     uint8_t* cbase = smem + S::kCtOff + j * S::kCtBytes;
     double2* ring = reinterpret_cast<double2*>(cbase + S::kAccBytes + S::kBaraBytes);
     const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
-    const uint32_t invfull = bar_base + (S::kInvFull + j * 2) * 8;
+    const uint32_t accready = bar_base + (S::kAccReady + j) * 8;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(cbase);
     Twiddles tw;
     make_twiddles(tw, u);
 
@@ -242,7 +211,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             const int s = rowc % STAGES;
             // test the slab's barrier now and consume the answer after the transform (mbarrier round trip off the critical path)
             const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1));
-            mbar_wait_warp(xfull + slot * 8, (rowc / XSLOTS) & 1);
+            mbar_wait_warp_long(xfull + slot * 8, (rowc / XSLOTS) & 1);
             const double2* buf = ring + slot * FFT_BUF;
             double2 v[8];
 #pragma unroll
@@ -270,10 +239,11 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             if (lane == 0) mbar_arrive(bar_base + (S::kBskEmpty + s) * 8);
             rowc++;
         }
-        // ---- first two passes of the inverse transforms; hand the result to the front warp through ring slots 0, 1.
-        // Both back warps must be done reading the step's forward rows before either overwrites a slot.
-        group_sync(j);
-        auto inverse_handoff = [&](double2 (&f)[8], int poly) {
+        // ---- inverse transforms, round to nearest, accumulate into acc (exact integers mod 2^32).  Exchange 1 of the
+        // inverse crosses the two back warps: it goes through ring slots 0 and 1, which are idle here (the front warp
+        // cannot produce the next step's rows before it has seen acc_ready).
+        group_sync(j);      // both back warps are done reading the step's forward rows
+        auto inverse_head = [&](double2 (&f)[8], int poly) {
             dft8<+1>(f);
             f[0] = cmul_conj(f[0], tw.h[0]);
 #pragma unroll
@@ -283,11 +253,32 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             double2* buf = ring + poly * FFT_BUF;
 #pragma unroll
             for (int q2 = 0; q2 < 8; q2++) buf[rr * 64 + lo + 8 * q2] = cmul_conj(f[q2], tw.g[q2]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(invfull + poly * 8);
         };
-        inverse_handoff(f0, 0);
-        inverse_handoff(f1, 1);
+        inverse_head(f0, 0);
+        inverse_head(f1, 1);
+        group_sync(j);
+#pragma unroll 1
+        for (int poly = 0; poly < 2; poly++) {
+            const double2* buf = ring + poly * FFT_BUF;
+            double2 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) v[r] = buf[r * 64 + u];
+            dft8<+1>(v);
+            v[0] = make_double2(v[0].x * (1.0 / 512.0), v[0].y * (1.0 / 512.0));
+#pragma unroll
+            for (int q = 1; q < 8; q++) {
+                double2 w = twist_const(q);
+                w.x *= (1.0 / 512.0); w.y *= (1.0 / 512.0);
+                v[q] = cmul_conj(v[q], w);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                acc[poly * N + u + 64 * q] += (uint32_t)__double2ll_rn(v[q].x);
+                acc[poly * N + u + 64 * q + NH] += (uint32_t)__double2ll_rn(v[q].y);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accready);
     }
 }
 
