@@ -13,6 +13,7 @@
 #include "../../include/redsec_b200.h"
 #include "blind_rotate.cuh"
 #include "blind_rotate_ws.cuh"
+#include "blind_rotate_tm.cuh"
 #include "lwe_kernels.cuh"
 #include "params.h"
 
@@ -100,7 +101,10 @@ int grow(rs_ctx* ctx, uint32_t** p, size_t* cap, size_t words) {
 // Blind-rotation variants: (ciphertext groups per CTA, BSK ring stages).  4 groups = 8 warps = 2 per SM
 // sub-partition (255 registers/thread).  More groups would put 3 warps on a sub-partition (168 registers/thread,
 // which spills).  Variant 0 (default) = warp-specialised kernel (blind_rotate_ws.cuh: 12 warps, front/back roles,
-// setmaxnreg); variant 1 = single-role kernel with a 7-stage BSK ring; variant 2 = same with a 4-stage ring.
+// setmaxnreg); variant 1 = single-role kernel with a 7-stage BSK ring; variant 2 = same with a 4-stage ring;
+// variant 3 = warp-specialised kernel with the BSK served from tensor memory (blind_rotate_tm.cuh: 16 warps,
+// front/back/producer roles; measured slower than variant 0, kept for the record -- see DESIGN.md);
+// variant 4 = variant 3 with a 4-stage smem ring.
 struct BrVariant { int groups, stages, smem; void (*set_attr)(cudaError_t*); };
 template <int G, int S>
 void br_launch(rs_ctx* ctx, int grid, const uint32_t* in, int count, uint32_t mu, uint32_t* ext) {
@@ -111,8 +115,9 @@ cudaError_t br_prepare() {
     return cudaFuncSetAttribute(rs::blind_rotate_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::BrSmem<G, S>::kTotal);
 }
 constexpr int kWsStages = 5, kWsSlots = 3;
-constexpr int kMaxSmemNeeded = rs::BrSmem<4, 7>::kTotal > rs::WsSmem<kWsStages, kWsSlots>::kTotal ? rs::BrSmem<4, 7>::kTotal
-                                                                                            : rs::WsSmem<kWsStages, kWsSlots>::kTotal;
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int kMaxSmemNeeded = cmax(cmax(rs::BrSmem<4, 7>::kTotal, rs::WsSmem<kWsStages, kWsSlots>::kTotal),
+                                    cmax(rs::TmSmem<5, 3>::kTotal, rs::TmSmem<5, 3>::kTotal));
 
 int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t count, uint32_t mu) {
     if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
@@ -121,7 +126,12 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
     const int grid = (int)((count + G - 1) / G);
     {
         LaunchScope ls(ctx, RS_K_BLIND_ROTATE);
-        if (ctx->br_variant == 0)
+        if (ctx->br_variant == 3)
+            rs::blind_rotate_tm_kernel<5, 3, 120, 184><<<grid, 512, rs::TmSmem<5, 3>::kTotal, ctx->stream>>>(
+                in, (int)count, mu, ctx->bsk_f, ext);
+        else if (ctx->br_variant == 4)
+            rs::blind_rotate_tm_kernel<4, 3, 120, 184><<<grid, 512, rs::TmSmem<5, 3>::kTotal, ctx->stream>>>(in, (int)count, mu, ctx->bsk_f, ext);
+        else if (ctx->br_variant == 0)
             rs::blind_rotate_ws_kernel<kWsStages, kWsSlots><<<grid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
                 in, (int)count, mu, ctx->bsk_f, ext);
         else if (ctx->br_variant == 1) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext);
@@ -187,10 +197,15 @@ int rs_ctx_create(rs_ctx** out, int device) {
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              rs::WsSmem<kWsStages, kWsSlots>::kTotal);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rs::blind_rotate_tm_kernel<5, 3, 120, 184>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 rs::TmSmem<5, 3>::kTotal);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rs::blind_rotate_tm_kernel<4, 3, 120, 184>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::TmSmem<5, 3>::kTotal);
     if (e == cudaSuccess) e = br_prepare<4, 7>();
     if (e == cudaSuccess) e = br_prepare<4, 4>();
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
-    if (const char* env = getenv("RS_BR_VARIANT")) { int v = atoi(env); if (v >= 0 && v <= 2) ctx->br_variant = v; }
+    if (const char* env = getenv("RS_BR_VARIANT")) { int v = atoi(env); if (v >= 0 && v <= 4) ctx->br_variant = v; }
     *out = ctx;
     return RS_OK;
 }
@@ -536,7 +551,7 @@ int rs_debug_stats(unsigned long long* out8, int reset) {
 #endif
 
 int rs_set_tuning(rs_ctx* ctx, int br_variant) {
-    if (!ctx || br_variant < 0 || br_variant > 2) return fail(ctx, RS_ERR_ARG, "rs_set_tuning: br_variant must be 0, 1 or 2");
+    if (!ctx || br_variant < 0 || br_variant > 4) return fail(ctx, RS_ERR_ARG, "rs_set_tuning: br_variant must be 0..4");
     ctx->br_variant = br_variant;
     return RS_OK;
 }

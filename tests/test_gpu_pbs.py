@@ -46,7 +46,7 @@ def test_pbs_bit_exact_and_decrypts(oracle, keyset, engine, count):
     assert np.array_equal(dec, np.where(bits == 1, 1, -1))
 
 
-@pytest.mark.parametrize("groups", [0, 1, 2])
+@pytest.mark.parametrize("groups", [0, 1, 2, 3, 4])
 def test_variants_agree(oracle, keyset, engine, groups):
     bits, ct = _rand_bits_ct(oracle, keyset, 29, MU8, 2.0 ** -25, 77)
     engine.set_tuning(groups)
