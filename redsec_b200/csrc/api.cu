@@ -36,7 +36,8 @@ struct rs_ctx {
     std::string err;
     // evaluation key, device resident
     double2* bsk_f = nullptr;     // [n][BK_ROWS][2][NH]
-    uint32_t* ksk = nullptr;      // [N][t][base][LWE_STRIDE]
+    uint32_t* ksk = nullptr;      // [N][t][base][LWE_STRIDE]  (un-tiled keyswitch, variant 1)
+    uint32_t* ksk7 = nullptr;     // [N][t][7][LWE_STRIDE]     (tiled keyswitch, default)
     bool key_loaded = false;
     // scratch (grow-only; no allocation on the steady-state hot path)
     uint32_t* ext = nullptr; size_t ext_cap = 0;        // extracted samples
@@ -51,6 +52,7 @@ struct rs_ctx {
     uint64_t prof_n[RS_K_COUNT] = {0, 0, 0, 0};
     uint64_t launches = 0;
     int br_variant = 0;
+    int ks_variant = 0;
 };
 
 namespace {
@@ -141,23 +143,42 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
     return RS_OK;
 }
 
-constexpr int kKsTile = 4;
-int launch_keyswitch(rs_ctx* ctx, uint32_t* out, const uint32_t* ext, size_t count) {
-    if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
-    if (count == 0) return RS_OK;
-    const int grid = (int)((count + kKsTile - 1) / kKsTile);
-    {
-        LaunchScope ls(ctx, RS_K_KEYSWITCH);
-        rs::keyswitch_kernel<kKsTile><<<grid, rs::LWE_STRIDE, 0, ctx->stream>>>(ext, (int)count, ctx->ksk, out);
-    }
-    RS_CUDA(ctx, cudaGetLastError());
-    return RS_OK;
-}
-
 int grid_for(rs_ctx* ctx, size_t total, int block) {
     size_t g = (total + block - 1) / block;
     size_t cap = (size_t)ctx->sm_count * 16;
     return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+constexpr int kKsTile = 4;
+template <int TILE>
+void ks_tiled_launch(rs_ctx* ctx, uint32_t* out, const uint32_t* ext, int count) {
+    // split the sum over i until the grid covers the machine about twice (partial sums are combined with red.add)
+    const int tiles = (count + TILE - 1) / TILE;
+    int ir = rs::KS_IR_MAX;
+    while (ir > 16 && tiles * (rs::N / ir) < 2 * ctx->sm_count) ir >>= 1;
+    dim3 grid((unsigned)tiles, (unsigned)(rs::N / ir));
+    rs::keyswitch_tiled_kernel<TILE><<<grid, 384, rs::KsSmem<TILE>::kTotal, ctx->stream>>>(ext, count, ir, ctx->ksk7, out);
+}
+int launch_keyswitch(rs_ctx* ctx, uint32_t* out, const uint32_t* ext, size_t count) {
+    if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
+    if (count == 0) return RS_OK;
+    if (ctx->ks_variant == 1) {
+        const int grid = (int)((count + kKsTile - 1) / kKsTile);
+        LaunchScope ls(ctx, RS_K_KEYSWITCH);
+        rs::keyswitch_kernel<kKsTile><<<grid, rs::LWE_STRIDE, 0, ctx->stream>>>(ext, (int)count, ctx->ksk, out);
+    } else {
+        {
+            LaunchScope ls(ctx, RS_K_KEYSWITCH);
+            rs::keyswitch_init_kernel<<<grid_for(ctx, count * rs::LWE_STRIDE, 256), 256, 0, ctx->stream>>>(ext, (int)count, out);
+        }
+        RS_CUDA(ctx, cudaGetLastError());
+        LaunchScope ls(ctx, RS_K_KEYSWITCH);
+        if (count >= 16384) ks_tiled_launch<64>(ctx, out, ext, (int)count);
+        else if (count >= 1024) ks_tiled_launch<32>(ctx, out, ext, (int)count);
+        else ks_tiled_launch<16>(ctx, out, ext, (int)count);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
 }
 
 // DFMA throughput probe: 8 independent chains per thread
@@ -202,9 +223,13 @@ int rs_ctx_create(rs_ctx** out, int device) {
                                  rs::TmSmem<5, 3>::kTotal);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(rs::blind_rotate_tm_kernel<4, 3, 120, 184>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::TmSmem<5, 3>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rs::keyswitch_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::KsSmem<64>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rs::keyswitch_tiled_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::KsSmem<32>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rs::keyswitch_tiled_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::KsSmem<16>::kTotal);
     if (e == cudaSuccess) e = br_prepare<4, 7>();
     if (e == cudaSuccess) e = br_prepare<4, 4>();
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
+    if (const char* env = getenv("RS_KS_VARIANT")) { int v = atoi(env); if (v == 0 || v == 1) ctx->ks_variant = v; }
     if (const char* env = getenv("RS_BR_VARIANT")) { int v = atoi(env); if (v >= 0 && v <= 4) ctx->br_variant = v; }
     *out = ctx;
     return RS_OK;
@@ -216,7 +241,7 @@ int rs_ctx_destroy(rs_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
-    cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->ext); cudaFree(ctx->lin); cudaFree(ctx->wire);
+    cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->ksk7); cudaFree(ctx->ext); cudaFree(ctx->lin); cudaFree(ctx->wire);
     cudaFree(ctx->io0); cudaFree(ctx->io1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -251,6 +276,7 @@ int rs_load_eval_key(rs_ctx* ctx, const uint32_t* bsk_host, const uint32_t* ksk_
     RS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->bsk_f) RS_CUDA(ctx, cudaMalloc(&ctx->bsk_f, rs::BSK_F_BYTES));
     if (!ctx->ksk) RS_CUDA(ctx, cudaMalloc(&ctx->ksk, rs::KSK_DEV_WORDS * sizeof(uint32_t)));
+    if (!ctx->ksk7) RS_CUDA(ctx, cudaMalloc(&ctx->ksk7, rs::KSK_TILED_WORDS * sizeof(uint32_t)));
     // staging for the torus32 keys (freed after conversion)
     uint32_t* stage = nullptr;
     const size_t ksk_bytes = RS_KSK_WORDS * sizeof(uint32_t), bsk_bytes = RS_BSK_WORDS * sizeof(uint32_t);
@@ -268,6 +294,12 @@ int rs_load_eval_key(rs_ctx* ctx, const uint32_t* bsk_host, const uint32_t* ksk_
     {
         LaunchScope ls(ctx, RS_K_OTHER);
         rs::ksk_pad_kernel<<<grid_for(ctx, rows * rs::LWE_STRIDE, 256), 256, 0, ctx->stream>>>(stage, ctx->ksk, rows);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    const size_t rows7 = (size_t)rs::N * rs::KS_T * rs::KS_DIGITS;
+    {
+        LaunchScope ls(ctx, RS_K_OTHER);
+        rs::ksk_tile_kernel<<<grid_for(ctx, rows7 * rs::LWE_STRIDE, 256), 256, 0, ctx->stream>>>(stage, ctx->ksk7, rows7);
     }
     RS_CUDA(ctx, cudaGetLastError());
     RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -549,6 +581,12 @@ int rs_debug_stats(unsigned long long* out8, int reset) {
     return 0;
 }
 #endif
+
+int rs_set_ks_variant(rs_ctx* ctx, int ks_variant) {
+    if (!ctx || ks_variant < 0 || ks_variant > 1) return fail(ctx, RS_ERR_ARG, "rs_set_ks_variant: 0 (tiled) or 1 (un-tiled)");
+    ctx->ks_variant = ks_variant;
+    return RS_OK;
+}
 
 int rs_set_tuning(rs_ctx* ctx, int br_variant) {
     if (!ctx || br_variant < 0 || br_variant > 4) return fail(ctx, RS_ERR_ARG, "rs_set_tuning: br_variant must be 0..4");

@@ -4,13 +4,157 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "params.h"
+#include "blind_rotate.cuh"   // mbarrier / TMA helpers
 
 namespace rs {
 
 // ---------------------------------------------------------------- keyswitch (TFHE lweKeySwitch)
-// res = (0, b') - sum_{i<N, j<t} KS[i][j][digit_ij]  where digit_ij = ((a'_i + prec_offset) >> (32-(j+1)*basebit)) & 7.
-// KS_TILE ciphertexts per CTA share every KSK row they pick through L1/L2; thread x owns output word x
-// of each ciphertext in the tile.  Device KSK layout: [N][t][base][LWE_STRIDE] (rows padded to 352 words).
+// res = (0, b') - sum_{i<N, j<t} KS[i][j][digit_ij]  where digit_ij = ((a'_i + prec_offset) >> (32-(j+1)*basebit)) & 7,
+// rows with digit 0 skipped (TFHE's `if (aij != 0)`).  Integer, bit-exact: uint32 adds commute, so any order and any
+// split of the sum gives the same words.
+//
+// Device KSK layout: [N][t][7][LWE_STRIDE] -- the digit-0 rows are never read and are dropped, rows padded to 352 words,
+// so the 3 x 7 rows of (i, j-triple) are one contiguous 29,568-byte block = one TMA bulk copy.
+//
+// keyswitch_tiled_kernel<TILE>: one CTA = TILE ciphertexts x `ir` consecutive coefficients i (grid.y = N/ir splits the
+// sum; partial sums are combined with red.global.add into rows pre-set to (0, b') by keyswitch_init_kernel).
+//   warp 11 (one lane) streams the KSK blocks of its i-range through a KS_STAGES-deep shared-memory ring (TMA +
+//   full/empty mbarriers); warps 0..10 = 352 threads = 4 groups of 88 uint4-lanes; group g owns TILE/4 ciphertexts and
+//   for each (i, j) subtracts the row its digit selects, read from SHARED memory (LDS.128, conflict-free).
+// Traffic per launch: L2 -> smem = (count/TILE) * 90.8 MB (each KSK byte once per tile, instead of count * 11.3 MB of
+// L1/L2 gathers in the un-tiled kernel below), smem -> registers = count * 11.3 MB.
+constexpr int KS_DIGITS = KS_BASE - 1;                                       // rows kept per (i, j)
+constexpr int KS_JGROUP = 3;                                                 // j's per ring stage
+constexpr int KS_STAGE_BYTES = KS_JGROUP * KS_DIGITS * LWE_STRIDE * 4;       // 29,568
+constexpr int KS_STAGES = 4;
+constexpr int KS_IR_MAX = 128;                                               // coefficients per CTA (abar tile in smem)
+constexpr size_t KSK_TILED_WORDS = (size_t)N * KS_T * KS_DIGITS * LWE_STRIDE;
+
+template <int TILE>
+struct KsSmem {
+    static constexpr int kStagesOff = 0;
+    static constexpr int kAbarOff = KS_STAGES * KS_STAGE_BYTES;
+    static constexpr int kBarOff = kAbarOff + KS_IR_MAX * TILE * 4;
+    static constexpr int kTotal = kBarOff + 2 * KS_STAGES * 8;
+};
+
+__global__ void keyswitch_init_kernel(const uint32_t* __restrict__ ext, int count, uint32_t* __restrict__ lwe_out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)count * LWE_STRIDE;
+    for (; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = idx / LWE_STRIDE;
+        const int x = (int)(idx % LWE_STRIDE);
+        lwe_out[idx] = (x == LWE_N) ? ext[c * EXT_STRIDE + N] : 0u;
+    }
+}
+
+template <int TILE>
+__global__ void __launch_bounds__(384, 1)
+keyswitch_tiled_kernel(const uint32_t* __restrict__ ext,      // [count][EXT_STRIDE]
+                       int count, int ir,                      // ir = coefficients per CTA, divides N, <= KS_IR_MAX
+                       const uint32_t* __restrict__ ksk7,      // [N][t][7][LWE_STRIDE]
+                       uint32_t* __restrict__ lwe_out)         // [count][LWE_STRIDE], pre-set to (0, b')
+{
+    using S = KsSmem<TILE>;
+    constexpr int CPG = TILE / 4;                              // ciphertexts per 88-lane group
+    static_assert(CPG % 4 == 0, "abar rows are read as uint4");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + S::kBarOff;          // full[KS_STAGES], empty[KS_STAGES]
+    uint32_t* abar = reinterpret_cast<uint32_t*>(smem + S::kAbarOff);      // [ir][TILE]
+    const int first = blockIdx.x * TILE;
+    const int tile = min(TILE, count - first);
+    const int i0 = blockIdx.y * ir;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nstages = ir * (KS_T / KS_JGROUP);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < KS_STAGES; s++) {
+            mbar_init(bar_base + s * 8, 1);
+            mbar_init(bar_base + (KS_STAGES + s) * 8, 11);     // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // a'_i + prec_offset for the tile, transposed to [i][ciphertext] (coalesced reads of ir consecutive words per row)
+    for (int idx = threadIdx.x; idx < ir * TILE; idx += blockDim.x) {
+        const int c = idx / ir, il = idx % ir;
+        abar[il * TILE + c] = (c < tile) ? ext[(size_t)(first + c) * EXT_STRIDE + i0 + il] + KS_PREC_OFFSET : 0u;   // 0 => all digits 0
+    }
+    __syncthreads();
+
+    if (warp == 11) {
+        if (lane == 0) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(ksk7) + (size_t)i0 * (KS_T / KS_JGROUP) * KS_STAGE_BYTES;
+#pragma unroll 1
+            for (int n = 0; n < nstages; n++) {
+                const int s = n % KS_STAGES;
+                if (n >= KS_STAGES) mbar_wait_thread(bar_base + (KS_STAGES + s) * 8, ((n - KS_STAGES) / KS_STAGES) & 1);
+                mbar_arrive_expect_tx(bar_base + s * 8, KS_STAGE_BYTES);
+                tma_load_1d(smem_base + S::kStagesOff + s * KS_STAGE_BYTES, src + (size_t)n * KS_STAGE_BYTES, KS_STAGE_BYTES, bar_base + s * 8);
+            }
+        }
+        return;
+    }
+
+    const int g = threadIdx.x / (LWE_STRIDE / 4);              // 88-lane group 0..3
+    const int l4 = threadIdx.x % (LWE_STRIDE / 4);             // uint4 lane within the row
+    uint4 acc[CPG];
+#pragma unroll
+    for (int c = 0; c < CPG; c++) acc[c] = make_uint4(0, 0, 0, 0);
+
+#pragma unroll 1
+    for (int n = 0; n < nstages; n++) {
+        const int s = n % KS_STAGES;
+        const int il = n / (KS_T / KS_JGROUP), jg = n % (KS_T / KS_JGROUP);
+        mbar_wait_warp(bar_base + s * 8, (n / KS_STAGES) & 1);
+        const uint4* rows = reinterpret_cast<const uint4*>(smem + S::kStagesOff + s * KS_STAGE_BYTES) + l4;
+        const uint4* ab4 = reinterpret_cast<const uint4*>(abar + il * TILE + g * CPG);
+#pragma unroll
+        for (int c4 = 0; c4 < CPG / 4; c4++) {
+            const uint4 a4 = ab4[c4];
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int jj = 0; jj < KS_JGROUP; jj++) {
+                    const int sh = 32 - (jg * KS_JGROUP + jj + 1) * KS_BASEBIT;
+                    const uint32_t d = (aw[k] >> sh) & (KS_BASE - 1);
+                    if (d) {
+                        const uint4 v = rows[(jj * KS_DIGITS + (int)d - 1) * (LWE_STRIDE / 4)];
+                        uint4& r = acc[c4 * 4 + k];
+                        r.x -= v.x; r.y -= v.y; r.z -= v.z; r.w -= v.w;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + (KS_STAGES + s) * 8);
+    }
+#pragma unroll
+    for (int c = 0; c < CPG; c++) {
+        const int ct = g * CPG + c;
+        if (ct < tile) {
+            uint32_t* o = lwe_out + (size_t)(first + ct) * LWE_STRIDE + 4 * l4;
+            atomicAdd(o + 0, acc[c].x); atomicAdd(o + 1, acc[c].y); atomicAdd(o + 2, acc[c].z); atomicAdd(o + 3, acc[c].w);
+        }
+    }
+}
+
+// KSK host layout [N][t][8][351] -> tiled device layout [N][t][7][352] (digit-0 rows dropped, rows zero-padded)
+__global__ void ksk_tile_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t rows7) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = rows7 * LWE_STRIDE;
+    for (; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r7 = idx / LWE_STRIDE;
+        const int x = (int)(idx % LWE_STRIDE);
+        const size_t ij = r7 / KS_DIGITS;
+        const int d = (int)(r7 % KS_DIGITS) + 1;
+        dst[idx] = x < LWE_WORDS ? src[(ij * KS_BASE + d) * LWE_WORDS + x] : 0u;
+    }
+}
+
+// Un-tiled reference kernel (first version; kept as variant for A/B checks): KS_TILE ciphertexts per CTA share every KSK
+// row they pick through L1/L2; thread x owns output word x.  Device KSK layout: [N][t][base][LWE_STRIDE].
 template <int KS_TILE>
 __global__ void __launch_bounds__(LWE_STRIDE)
 keyswitch_kernel(const uint32_t* __restrict__ ext,      // [count][EXT_STRIDE]

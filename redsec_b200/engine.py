@@ -192,6 +192,9 @@ class Engine:
     def set_tuning(self, br_variant: int):
         self._chk(self.lib.rs_set_tuning(self.ctx, br_variant))
 
+    def set_ks_variant(self, ks_variant: int):
+        self._chk(self.lib.rs_set_ks_variant(self.ctx, ks_variant))
+
     def device_info(self):
         sm, ma, mi, sh = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
         self._chk(self.lib.rs_device_info(self.ctx, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(sh)))

@@ -1,7 +1,7 @@
 # usage: bash scripts/gpu_variants.sh "0 3 4"  -- parity of the blind-rotate variants, then blind-rotate / keyswitch timings per variant
 VARS=${1:-"0 3 4"}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_pbs.py -x -q -k "variants or blind_rotate or pbs_bit_exact" 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_gpu_pbs.py -x -q 2>&1 | tail -15
 RS_VARS="$VARS" timeout 600 python - <<'PY' 2>&1 | tee gpurun_out/variants_perf.log
 import os, sys, time, numpy as np
 sys.path.insert(0, '.')
