@@ -206,6 +206,34 @@ def plain_forward(layers, pixels, enc_conv_semantics=False, collect=None):
     return x
 
 
+def plain_layer_preact(L, x_in):
+    """Pre-activation integers [h][w][c] of ONE layer of the plaintext twin for the inputs that layer receives
+    (bits 0/1 for a BinLayer, integers for an IntLayer); `encrypted` conventions for IntLayer convs.  Used by the
+    full-size teacher-forced check: feed the DECRYPTED inputs of an encrypted layer, compare signs away from 0."""
+    ls = L.spec
+    x = np.asarray(x_in, dtype=np.int64)
+    if ls["kind"] == "bin":
+        x = 2 * x - 1
+    if L.has_conv:
+        x = x.reshape(L.cin)
+        term = np.int64(-1) if ls["kind"] == "int" else None
+        x = _conv(L, x, term, term)
+    else:
+        x = x.reshape((L.sp_in if L.has_sumpool else L.q_dims[:2]) + (L.q_dims[2],))
+    if L.has_sumpool:
+        x = _sumpool(L, x)
+    return x.reshape(L.q_dims) + L.bias.astype(np.int64)
+
+
+def plain_maxpool(L, bits):
+    ph_, pw_, sh, sw, oh, ow = L.mp_geom
+    y = np.zeros((oh, ow, bits.shape[2]), dtype=bits.dtype)
+    for a in range(oh):
+        for b in range(ow):
+            y[a, b] = bits[a * sh: a * sh + ph_, b * sw: b * sw + pw_].reshape(-1, bits.shape[2]).max(axis=0)
+    return y
+
+
 # ----------------------------------------------------------------------------------------------- encrypted CPU path
 def enc_linear(L, ct):
     """Bootstrap-free part of one layer on LWE rows [count][351] -> [(h,w,c) flat][351] (uint32 wrap-around)."""

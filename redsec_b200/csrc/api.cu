@@ -53,6 +53,7 @@ struct rs_ctx {
     uint64_t launches = 0;
     int br_variant = 0;
     int ks_variant = 0;
+    float l2_keep = 0.f;          // fraction of the BSK stream hinted L2 evict_last
 };
 
 namespace {
@@ -135,7 +136,7 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
             rs::blind_rotate_tm_kernel<4, 3, 120, 184><<<grid, 512, rs::TmSmem<5, 3>::kTotal, ctx->stream>>>(in, (int)count, mu, ctx->bsk_f, ext);
         else if (ctx->br_variant == 0)
             rs::blind_rotate_ws_kernel<kWsStages, kWsSlots><<<grid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
-                in, (int)count, mu, ctx->bsk_f, ext);
+                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep);
         else if (ctx->br_variant == 1) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext);
         else br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext);
     }
@@ -229,6 +230,11 @@ int rs_ctx_create(rs_ctx** out, int device) {
     if (e == cudaSuccess) e = br_prepare<4, 7>();
     if (e == cudaSuccess) e = br_prepare<4, 4>();
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
+    if (const char* env = getenv("RS_L2_KEEP")) { float v = (float)atof(env); if (v >= 0.f && v <= 1.f) ctx->l2_keep = v; }
+    if (ctx->l2_keep > 0.f) {
+        cudaError_t le = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
+        fprintf(stderr, "[rs] persisting L2 max %d B, set: %s\n", prop.persistingL2CacheMaxSize, cudaGetErrorString(le));
+    }
     if (const char* env = getenv("RS_KS_VARIANT")) { int v = atoi(env); if (v == 0 || v == 1) ctx->ks_variant = v; }
     if (const char* env = getenv("RS_BR_VARIANT")) { int v = atoi(env); if (v >= 0 && v <= 4) ctx->br_variant = v; }
     *out = ctx;

@@ -105,6 +105,19 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_g
                  "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
 
+// L2 residency hint for the BSK stream: the 114.7 MB Fourier key is walked cyclically once per wave of CTAs, which is the
+// worst case for an LRU-like 126 MB L2 shared with the ciphertext traffic (measured: every wave re-read the whole key from
+// HBM, 12.8 GB per 2^16-ciphertext launch).  Marking a FRACTION of the lines evict_last pins that part across waves.
+__device__ __forceinline__ uint64_t l2_policy_evict_last(float fraction) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, %1;" : "=l"(pol) : "f"(fraction));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+
 // ---------------------------------------------------------------- shared-memory plan
 template <int GROUPS, int STAGES>
 struct BrSmem {   // STAGES = depth of the BSK slab ring

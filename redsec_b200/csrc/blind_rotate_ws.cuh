@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(384, 1)
 blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRIDE]
                        int count, uint32_t mu,
                        const double2* __restrict__ bsk_f,       // [n][BK_ROWS][2][NH]
-                       uint32_t* __restrict__ ext_out)          // [count][EXT_STRIDE]
+                       uint32_t* __restrict__ ext_out,          // [count][EXT_STRIDE]
+                       float l2_keep)                           // fraction of the BSK stream marked L2 evict_last (0 = no hint)
 {
     using S = WsSmem<STAGES, XSLOTS>;
     constexpr int AHEAD = 1;                       // a front warp starting row r makes sure slabs <= r+AHEAD are requested
@@ -105,6 +106,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
         const uint32_t accready = bar_base + (S::kAccReady + j) * 8;
         const uint8_t* bsk_bytes = reinterpret_cast<const uint8_t*>(bsk_f);
+        const uint64_t l2pol = l2_policy_evict_last(l2_keep);
 
         // ---- modswitch and accumulator init (step 2)
         const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
@@ -145,8 +147,12 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                                 if (cur >= STAGES)
                                     mbar_wait_thread(bar_base + (S::kBskEmpty + ns) * 8, ((cur - STAGES) / STAGES) & 1);
                                 mbar_arrive_expect_tx(bar_base + (S::kBskFull + ns) * 8, S::kStageBytes);
-                                tma_load_1d(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
-                                            S::kStageBytes, bar_base + (S::kBskFull + ns) * 8);
+                                if (l2_keep > 0.f)
+                                    tma_load_1d_hint(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
+                                                     S::kStageBytes, bar_base + (S::kBskFull + ns) * 8, l2pol);
+                                else
+                                    tma_load_1d(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
+                                                S::kStageBytes, bar_base + (S::kBskFull + ns) * 8);
                                 cur++;
                             } else {
                                 cur = prev;

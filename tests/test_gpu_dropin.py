@@ -1,0 +1,50 @@
+"""Drop-in check (SURVEY 8b "B-outer", row f3): the reference's own, UNMODIFIED GPU drivers (nets/*/main.cu + net.cu, built by
+dropin/build.sh with the reference Makefile's command lines against this repo's REDcuFHE facade) run on the GPU box and must
+write the same output ciphertexts as the engine's own EncryptedNet on the same keyset and image ciphertexts."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from redsec_b200 import netspec
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TREE = os.path.join(ROOT, "dropin", "_build", "tree")
+
+
+@pytest.mark.parametrize("name", ["mnist/sign1024x1", "mnist/sign1024x3", "cifar/binarynet_small"])
+def test_reference_gpu_driver_runs_on_the_engine(engine, keyset, name):
+    from redsec_b200 import client, nets
+    exe = os.path.join(TREE, "nets", name, "gpu-encrypt.out")
+    if not os.path.exists(exe):
+        pytest.skip("dropin/_build is not built (needs the reference tree at build time: dropin/build.sh)")
+    cdir = os.path.join(TREE, "client")
+    os.makedirs(cdir, exist_ok=True)
+    ks = client.KeySet(keyset.lwe_key, keyset.tlwe_key, keyset.bsk, keyset.ksk)
+    eval_key = os.path.join(cdir, "eval.key")
+    if not os.path.exists(eval_key):
+        client.write_keys(ks, os.path.join(cdir, "secret.key"), eval_key)
+    spec = netspec.NETS[name]()
+    label, px = netspec.load_image_csv(spec["image"])
+    ct = client.encrypt_image(px, ks.lwe_key, seed=11)
+    client.write_ctxt(os.path.join(cdir, "image.ctxt"), ct, variance=2.0 ** -30)
+    out_path = os.path.join(cdir, "network_output.ctxt")
+    if os.path.exists(out_path):
+        os.remove(out_path)                      # the driver appends (main.cu:82)
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.pathsep.join([os.path.join(ROOT, "dropin", "_build", "lib"), os.path.join(ROOT, "redsec_b200"),
+                                              env.get("LD_LIBRARY_PATH", "")])
+    r = subprocess.run([exe], cwd=os.path.dirname(exe), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Inference Time" in r.stdout
+    got = client.read_ctxt(out_path, 10)
+    net = nets.EncryptedNet(engine, spec)
+    want = engine.download(net.run(engine.upload(ct)))
+    net.close()
+    assert np.array_equal(got, want), "reference driver over the facade and EncryptedNet disagree"
+    scores = client.decrypt(got, ks.lwe_key, 4096)
+    print(name, "scores", scores.tolist(), "label", label, r.stdout.strip().splitlines()[-1])
+    if name.startswith("mnist"):
+        assert int(np.argmax(scores)) == label

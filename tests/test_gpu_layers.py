@@ -118,3 +118,55 @@ def test_builder_cnn_int_conv_bit_exact(oracle, keyset, engine):
     y1, _, _ = net.layer_forward(1, y0)
     assert np.array_equal(engine.download(y1), want1)
     net.close()
+
+
+@pytest.mark.parametrize("name", ["cifar/binarynet_small"])
+def test_full_size_cifar_teacher_forced_signs(oracle, keyset, engine, name):
+    """Full-size property check (the oracle cannot bootstrap 320k neurons in test time): run the whole encrypted CIFAR net
+    on the GPU, then for EVERY layer decrypt its input, recompute the layer's integer pre-activations with the plaintext
+    twin, and require every output bit whose |pre-activation| clears the modswitch-noise margin to carry the right sign
+    (sigma of the 2N-rounding is 7.7 message units; margin 48 = 6 sigma).  Max-pool outputs must equal the OR
+    of their window whenever all four window elements are decidable.  Final scores must match to rounding noise."""
+    from oracle import layers_oracle as LO
+    nets = _nets()
+    spec = netspec.NETS[name]()
+    label, px = netspec.load_image_csv(spec["image"])
+    ct = oracle.encrypt(LO.encode_pixels(px), 2.0 ** -15, keyset.lwe_key, 45)
+    layers = LO.prepare(spec, spec["weights"])
+    net = nets.EncryptedNet(engine, spec)
+    assert net.bootstraps() == LO.count_bootstraps(layers)
+    outs = []
+    net.run(engine.upload(ct), collect=outs)
+    net.close()
+    MARGIN = 48
+    # phase noise of the rounding to 2N = 2048: one uniform error of width 1/2048 per key bit set (+1 for b), in units of 1/4096
+    sigma = float(np.sqrt((int(np.sum(keyset.lwe_key)) + 1) / 12.0) * 2.0)
+    from math import erfc, sqrt
+    phi = np.vectorize(lambda z: 0.5 * erfc(z / sqrt(2.0)))
+    x_in = 2 * np.asarray(px, dtype=np.int64) - 255                     # what layer 0 receives
+    flips = expected = 0.0
+    for L, out in zip(layers, outs):
+        pre = LO.plain_layer_preact(L, x_in)
+        dec = oracle.decrypt(out, keyset.lwe_key, 4096)
+        if L.spec["act"] == "none":
+            assert np.max(np.abs(dec - pre.reshape(-1))) <= 3, "final scores differ from the plaintext twin on the same decrypted inputs"
+            break
+        assert set(np.unique(dec)) <= {-1, 1}, "bridged bits must decrypt to +-1/4096"
+        got = (dec > 0).astype(np.int64)
+        want = (pre >= 0).astype(np.int64)
+        sure = np.abs(pre) >= MARGIN
+        if L.has_maxpool:
+            got = got.reshape(L.out_dims)
+            sure = 1 - LO.plain_maxpool(L, 1 - sure.astype(np.int64))       # window decidable iff all four are
+            want = LO.plain_maxpool(L, want)
+            ok = (got == want) | (sure == 0)
+        else:
+            got = got.reshape(L.q_dims)
+            ok = (got == want) | ~sure
+            # the undecidable neurons must flip as often as the rounding noise predicts: P(flip) = Phi(-|pre + 1/2| / sigma)
+            flips += float(np.count_nonzero(got != want))
+            expected += float(phi(np.abs(pre + 0.5) / sigma).sum())
+        x_in = got.reshape(-1)
+        assert ok.all(), f"{int((~ok).sum())} neurons with |pre-activation| >= {MARGIN} carry the wrong sign"
+    print(f"near-threshold sign flips: observed {flips:.0f}, predicted by the 2N-rounding noise model {expected:.0f} (sigma {sigma:.2f} units)")
+    assert expected > 100 and 0.8 < flips / expected < 1.25, (flips, expected)
