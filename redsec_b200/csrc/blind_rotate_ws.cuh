@@ -206,6 +206,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     make_twiddles(tw, u);
 
     int rowc = 0;
+    uint32_t row_ready = 0;     // non-blocking test of the NEXT row's exchange slot, issued one row early (see below)
 #pragma unroll 1
     for (int i = 0; i < LWE_N; i++) {
         double2 f0[8], f1[8];   // Fourier accumulators for the two output polynomials
@@ -217,7 +218,8 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             const int s = rowc % STAGES;
             // test the slab's barrier now and consume the answer after the transform (mbarrier round trip off the critical path)
             const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1));
-            mbar_wait_warp_long(xfull + slot * 8, (rowc / XSLOTS) & 1);
+            // the row's exchange slot was tested before the previous row's MAC; only a miss pays the mbarrier round trip here
+            if (!__all_sync(0xffffffffu, row_ready)) mbar_wait_warp_long(xfull + slot * 8, (rowc / XSLOTS) & 1);
             const double2* buf = ring + slot * FFT_BUF;
             double2 v[8];
 #pragma unroll
@@ -226,11 +228,18 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             __syncwarp();
             if (lane == 0) mbar_arrive(xempty + slot * 8);      // the row has been consumed into registers
             rotate_exchange(v, lo);
+            // the first BSK operands are requested before pass 3 when the slab is already resident (the common case), so that
+            // their shared-memory latency overlaps the butterflies instead of stalling the first FMA of the MAC
+            const double2* B = reinterpret_cast<const double2*>(smem + S::kStagesOff + s * S::kStageBytes) + u;
+            double2 b0, b1;
+            if (slab_ready) { b0 = B[0]; b1 = B[NH]; }
             dft8_twiddled<+1, false>(v, [&](int k) { return tw.h[k]; });
 
-            if (!slab_ready) mbar_wait_warp(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1);
-            const double2* B = reinterpret_cast<const double2*>(smem + S::kStagesOff + s * S::kStageBytes) + u;
-            double2 b0 = B[0], b1 = B[NH];
+            if (!slab_ready) {
+                mbar_wait_warp(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1);
+                b0 = B[0]; b1 = B[NH];
+            }
+            row_ready = mbar_test(xfull + ((rowc + 1) % XSLOTS) * 8, ((rowc + 1) / XSLOTS) & 1);   // consumed at the next row's start
 #pragma unroll
             for (int x = 0; x < 8; x++) {
                 double2 n0, n1;
