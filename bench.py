@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 GATES_PER_STEP = 1 << 16
 FLOP_PER_PBS = 258.4e6            # 350 x (22 x 26112 + 163840)
 BSK_FOURIER_BYTES = 114_688_000   # streamed once per wave of CTAs
+KSK_TILED_BYTES = 1024 * 9 * 7 * 352 * 4   # device keyswitch table (digit-0 rows dropped)
 LWE_WIRE_BYTES = 351 * 4
 WORKLOAD = "gate microbench: 2^16 independent bootstrapped gates per step per GPU (NAND even steps / XNOR odd steps), keyset n=350 N=1024 l=10 Bgbit=3 t=9"
 
@@ -187,6 +188,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     ks = client.keygen(0)
     eng.load_eval_key(ks.bsk, ks.ksk)
     fp64_peak = eng.fp64_peak_tflops()
+    fp64_peak3 = eng.fp64_peak_three_operand_tflops()
 
     G = args.gates
     rng = np.random.default_rng(1 + rank)        # i.i.d. Bernoulli(1/2) inputs, alpha = 2^-25
@@ -272,7 +274,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             try:
                 tj = json.load(open(tp))
                 if tj.get("gates_per_launch") == G:
-                    traffic = tj.get("dram_bytes_per_launch")
+                    traffic = tj.get("blind_rotate_dram_bytes_per_launch")
             except Exception:
                 pass
         peaks = {}
@@ -294,12 +296,21 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp64_peak, "traffic": traffic,
-                         "kernel": "blind_rotate_kernel", "launch_ms": br_avg_s * 1e3, "launches": int(br_n),
+                         "kernel": "blind_rotate_ws_kernel", "launch_ms": br_avg_s * 1e3, "launches": int(br_n),
                          "algorithmic_flop_per_launch": FLOP_PER_PBS * G,
-                         "peak_source": "measured live by rs_fp64_peak (dependent-free DFMA loop, all SMs); MEASURED_PEAKS.json has no FP64 figure",
+                         "peak_source": "measured live by rs_fp64_peak (dependent-free DFMA loop with constant operands, all SMs); MEASURED_PEAKS.json has no FP64 figure",
+                         "peak_three_register_fma": fp64_peak3,
+                         "frac_of_three_register_fma_peak": achieved_tflops / fp64_peak3,
+                         "note": "a DFMA with three distinct register operands issues every 3 cycles instead of 2 (register-file bound, scripts/probes/fp64_probe2.cu); "
+                                 "peak_three_register_fma is that rate measured live, the ceiling of the MAC and twiddle FMAs",
+                         "traffic_note": "DRAM bytes of one 2^16-ciphertext blind-rotate launch from ncu (profiles/r1_traffic.json); the Fourier BSK is re-streamed "
+                                         "about once per 2 waves of CTAs; the algorithmic bytes count it once; HBM use stays below 1 % of peak either way",
                          "hbm": {"algorithmic_bytes_per_launch": BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4),
                                  "achieved_gbs": (BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4)) / br_avg_s / 1e9,
                                  "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+                         "keyswitch": {"kernel": "keyswitch_tiled_kernel", "launch_ms": ks_ms / max(ks_n / 2, 1),
+                                       "bound": "shared-memory bandwidth", "smem_read_bytes_per_launch": G * 9216 * 7 / 8 * 1408,
+                                       "l2_to_smem_bytes_per_launch": (G // 64) * KSK_TILED_BYTES},
                          "step_share": {"blind_rotate_ms": br_ms / args.steps, "keyswitch_ms": ks_ms / args.steps,
                                         "linear_ms": lin_ms / args.steps}},
             "cpu_baseline": cpu,

@@ -67,6 +67,7 @@ SIGNATURES = {
     "rs_profile_reset": (C.c_int, [vp]),
     "rs_launch_count": (C.c_uint64, [vp]),
     "rs_fp64_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
+    "rs_fp64_peak_three_operand": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "rs_set_tuning": (C.c_int, [vp, C.c_int]),
     "rs_set_ks_variant": (C.c_int, [vp, C.c_int]),
     "rs_device_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),

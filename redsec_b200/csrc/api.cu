@@ -193,6 +193,20 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// same loop with three distinct register operands per FMA: the register file feeds the FP64 pipe one fresh 64-bit operand
+// per cycle, so such an FMA takes 3 cycles instead of 2 (scripts/probes/fp64_probe2.cu) -- the practical ceiling of FMA-heavy code
+__global__ void fp64_peak3_kernel(double* out, const double* in, int iters) {
+    double a[8], b[8], c[8];
+    for (int i = 0; i < 8; i++) { a[i] = in[i] + threadIdx.x; b[i] = in[8 + i] + threadIdx.x; c[i] = in[16 + i] + 1e-9 * threadIdx.x; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = fma(b[i], c[i], a[i]);
+    }
+    double s = 0;
+    for (int i = 0; i < 8; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -562,6 +576,32 @@ int rs_fp64_peak(rs_ctx* ctx, double* tflops) {
         if (rep > 0 && ms < best) best = ms;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = 2.0 * 8.0 * (double)iters * grid * block / (best * 1e-3) / 1e12;
+    return RS_OK;
+}
+
+int rs_fp64_peak_three_operand(rs_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return fail(ctx, RS_ERR_ARG, "rs_fp64_peak_three_operand: NULL argument");
+    const int block = 256, grid = ctx->sm_count * 8, iters = 20000;
+    double *out = nullptr, *in = nullptr;
+    RS_CUDA(ctx, cudaMalloc(&out, (size_t)grid * block * sizeof(double)));
+    RS_CUDA(ctx, cudaMalloc(&in, 32 * sizeof(double)));
+    RS_CUDA(ctx, cudaMemsetAsync(in, 0, 32 * sizeof(double), ctx->stream));
+    cudaEvent_t e0, e1;
+    RS_CUDA(ctx, cudaEventCreate(&e0));
+    RS_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        RS_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        fp64_peak3_kernel<<<grid, block, 0, ctx->stream>>>(out, in, iters);
+        ctx->launches++;
+        RS_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        RS_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out); cudaFree(in);
     *tflops = 2.0 * 8.0 * (double)iters * grid * block / (best * 1e-3) / 1e12;
     return RS_OK;
 }

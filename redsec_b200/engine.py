@@ -189,6 +189,11 @@ class Engine:
         self._chk(self.lib.rs_fp64_peak(self.ctx, C.byref(v)))
         return v.value
 
+    def fp64_peak_three_operand_tflops(self) -> float:
+        v = C.c_double()
+        self._chk(self.lib.rs_fp64_peak_three_operand(self.ctx, C.byref(v)))
+        return v.value
+
     def set_tuning(self, br_variant: int):
         self._chk(self.lib.rs_set_tuning(self.ctx, br_variant))
 
