@@ -47,7 +47,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + _sources() + ["-lgomp"]
+    extra = os.environ.get("RS_NVCC_EXTRA", "").split()      # e.g. -DRS_WAIT_HINT_NS=200u for tuning experiments
+    cmd = [NVCC] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + _sources() + ["-lgomp"]
     env = dict(os.environ)
     # the image exports CC/CXX=/opt/gcc/bin/* (a wrapper without OpenMP specs); use the system g++ as nvcc's host compiler
     cmd[1:1] = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []

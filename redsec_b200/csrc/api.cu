@@ -2,6 +2,7 @@
 // Replaces lib/GPU/gates.cu + libredcufhe for the bootstrap hot path (SURVEY.md 8b "B-inner").
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -127,6 +128,9 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
     if (count == 0) return RS_OK;
     constexpr int G = 4;
     const int grid = (int)((count + G - 1) / G);
+    // warp-specialised kernels partition the batch evenly over the grid; a batch below one wave (the 196-neuron MNIST layer)
+    // is spread over all SMs at 1-2 ciphertexts per CTA: a wave with <= 2 ciphertexts per SM takes 6.1 ms instead of 7.9
+    const int bgrid = count < (size_t)G * ctx->sm_count ? (int)std::min<size_t>(count, (size_t)ctx->sm_count) : grid;
     {
         LaunchScope ls(ctx, RS_K_BLIND_ROTATE);
         if (ctx->br_variant == 3)
@@ -135,7 +139,7 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
         else if (ctx->br_variant == 4)
             rs::blind_rotate_tm_kernel<4, 3, 120, 184><<<grid, 512, rs::TmSmem<5, 3>::kTotal, ctx->stream>>>(in, (int)count, mu, ctx->bsk_f, ext);
         else if (ctx->br_variant == 0)
-            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots><<<grid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
+            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
                 in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep);
         else if (ctx->br_variant == 1) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext);
         else br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext);
@@ -605,6 +609,13 @@ int rs_fp64_peak_three_operand(rs_ctx* ctx, double* tflops) {
     *tflops = 2.0 * 8.0 * (double)iters * grid * block / (best * 1e-3) / 1e12;
     return RS_OK;
 }
+
+#ifdef RS_WS_PROF
+int rs_debug_ws_prof(long long* out96) {   // debug builds only: phase timers of CTA 0, [12 warps][8 phases]
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out96, rs::g_ws_prof, sizeof(long long) * 96) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 #ifdef RS_BR_STATS
 int* rs_debug_progress() {   // host-mapped progress words of block 0 (debug builds only)

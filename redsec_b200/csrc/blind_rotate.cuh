@@ -73,12 +73,15 @@ __device__ __forceinline__ uint32_t mbar_try_hint(uint32_t bar, uint32_t parity,
         "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
     return ok;
 }
+#ifndef RS_WAIT_HINT_NS
+#define RS_WAIT_HINT_NS 2000u
+#endif
 // as mbar_wait_warp, for waits that are expected to last (pipeline hand-offs): polls with a suspend-time hint so that
 // the waiting warp does not burn issue slots its neighbours need.
 __device__ __forceinline__ void mbar_wait_warp_long(uint32_t bar, uint32_t parity) {
     if (__all_sync(0xffffffffu, mbar_try(bar, parity))) return;
     const long long t0 = clock64();
-    while (!__all_sync(0xffffffffu, mbar_try_hint(bar, parity, 2000u))) {
+    while (!__all_sync(0xffffffffu, mbar_try_hint(bar, parity, RS_WAIT_HINT_NS))) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }

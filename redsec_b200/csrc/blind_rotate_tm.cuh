@@ -119,8 +119,10 @@ blind_rotate_tm_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + S::kBarOff;
 
-    const int first_ct = blockIdx.x * S::kCts;
-    const int active = min(S::kCts, count - first_ct);
+    // balanced partition: CTA b owns ciphertexts [b*count/grid, (b+1)*count/grid) -- 3 or 4 each when the host sizes the grid
+    // as whole waves of SMs (launch_blind_rotate), fewer for small batches so that every SM gets work
+    const int first_ct = (int)((long long)blockIdx.x * count / gridDim.x);
+    const int active = (int)((long long)(blockIdx.x + 1) * count / gridDim.x) - first_ct;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 

@@ -29,6 +29,19 @@
 
 namespace rs {
 
+#ifdef RS_WS_PROF
+// per-warp phase timers of CTA 0 (debug builds only: RS_NVCC_EXTRA=-DRS_WS_PROF, read with scripts/ws_prof.py):
+// [warp][phase] accumulated clock64 cycles.  Results: profiles/r1_ws_phase_timers.txt
+__device__ long long g_ws_prof[12][8];
+#define WSP_DECL long long wsp_t = clock64(), wsp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define WSP(phase) do { const long long n_ = clock64(); wsp_acc[phase] += n_ - wsp_t; wsp_t = n_; } while (0)
+#define WSP_FLUSH() do { if (blockIdx.x == 0 && lane == 0) for (int q_ = 0; q_ < 8; q_++) g_ws_prof[warp][q_] = wsp_acc[q_]; } while (0)
+#else
+#define WSP_DECL
+#define WSP(phase) do { } while (0)
+#define WSP_FLUSH() do { } while (0)
+#endif
+
 template <int STAGES, int XSLOTS>
 struct WsSmem {
     static constexpr int kCts = 4;
@@ -71,8 +84,10 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     const uint32_t bar_base = smem_base + S::kBarOff;
     int* issued = reinterpret_cast<int*>(smem + S::kIssuedOff);
 
-    const int first_ct = blockIdx.x * S::kCts;
-    const int active = min(S::kCts, count - first_ct);
+    // balanced partition: CTA b owns ciphertexts [b*count/grid, (b+1)*count/grid): 4 each (fewer in the last CTAs) for the
+    // usual grid of ceil(count/4), 1-2 each when the host spreads a batch smaller than one wave over all SMs
+    const int first_ct = (int)((long long)blockIdx.x * count / gridDim.x);
+    const int active = (int)((long long)(blockIdx.x + 1) * count / gridDim.x) - first_ct;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -119,9 +134,12 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         __syncwarp();
 
         int rowc = 0;    // rows produced by this front warp (= BSK slab index of the row)
+        WSP_DECL;
 #pragma unroll 1
         for (int i = 0; i < LWE_N; i++) {
+            WSP(7);
             if (i > 0) mbar_wait_warp_long(accready, (i - 1) & 1);   // back warps have added step i-1 into the accumulator
+            WSP(0);
             const int a = bara[i];
 #pragma unroll 1
             for (int c = 0; c < 2; c++) {
@@ -135,6 +153,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                     }
                 }
 #pragma unroll 1
+                WSP(1);
                 for (int p = 0; p < BK_L; p++) {
                     // ---- BSK producer duty (claimed in order by whichever front warp gets here first)
                     if (lane == 0) {
@@ -160,9 +179,11 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                         }
                     }
                     __syncwarp();
+                    WSP(2);
                     // ---- ring slot: wait until both back warps have read its previous occupant
                     const int slot = rowc % XSLOTS;
                     if (rowc >= XSLOTS) mbar_wait_warp(xempty + slot * 8, ((rowc - XSLOTS) / XSLOTS) & 1);
+                    WSP(3);
                     double2* buf = ring + slot * FFT_BUF;
                     const DigitLevel dl = digit_level(p);
 #pragma unroll
@@ -180,9 +201,11 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                     __syncwarp();
                     if (lane == 0) mbar_arrive(xfull + slot * 8);
                     rowc++;
+                    WSP(4);
                 }
             }
         }
+        WSP_FLUSH();
         mbar_wait_warp_long(accready, (LWE_N - 1) & 1);     // the last step's accumulator update
         // ---- sample extract: a'[0]=acc_a[0], a'[k]=-acc_a[N-k], b'=acc_b[0]
         uint32_t* ext = ext_out + (size_t)ct * EXT_STRIDE;
@@ -207,6 +230,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
 
     int rowc = 0;
     uint32_t row_ready = 0;     // non-blocking test of the NEXT row's exchange slot, issued one row early (see below)
+    WSP_DECL;
 #pragma unroll 1
     for (int i = 0; i < LWE_N; i++) {
         double2 f0[8], f1[8];   // Fourier accumulators for the two output polynomials
@@ -219,7 +243,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             // test the slab's barrier now and consume the answer after the transform (mbarrier round trip off the critical path)
             const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1));
             // the row's exchange slot was tested before the previous row's MAC; only a miss pays the mbarrier round trip here
+            WSP(7);
             if (!__all_sync(0xffffffffu, row_ready)) mbar_wait_warp_long(xfull + slot * 8, (rowc / XSLOTS) & 1);
+            WSP(0);
             const double2* buf = ring + slot * FFT_BUF;
             double2 v[8];
 #pragma unroll
@@ -235,10 +261,12 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             if (slab_ready) { b0 = B[0]; b1 = B[NH]; }
             dft8_twiddled<+1, false>(v, [&](int k) { return tw.h[k]; });
 
+            WSP(1);
             if (!slab_ready) {
                 mbar_wait_warp(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1);
                 b0 = B[0]; b1 = B[NH];
             }
+            WSP(2);
             row_ready = mbar_test(xfull + ((rowc + 1) % XSLOTS) * 8, ((rowc + 1) / XSLOTS) & 1);   // consumed at the next row's start
 #pragma unroll
             for (int x = 0; x < 8; x++) {
@@ -253,6 +281,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_base + (S::kBskEmpty + s) * 8);
             rowc++;
+            WSP(3);
         }
         // ---- inverse transforms, round to nearest, accumulate into acc (exact integers mod 2^32).  Exchange 1 of the
         // inverse crosses the two back warps: it goes through ring slots 0 and 1, which are idle here (the front warp
@@ -294,7 +323,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(accready);
+        WSP(4);
     }
+    WSP_FLUSH();
 }
 
 }  // namespace rs

@@ -12,7 +12,7 @@ eng = rs.Engine(0)
 eng.load_eval_key(ks.bsk, ks.ksk)
 for variant in [int(v) for v in os.environ["RS_VARS"].split()]:
     eng.set_tuning(variant)
-    for count in (592, 8192, 65536):
+    for count in (148, 592, 1024, 65536):
         ct = O.encrypt(np.full(count, 0x20000000), 2.0**-25, ks.lwe_key, 3)
         dev = eng.upload(ct); out = eng.alloc(count)
         eng.pbs(dev, 0x20000000, out); eng.sync()
