@@ -152,8 +152,8 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                         src[hf][2 * q + 1] = rot_diff(acc + c * N, lane + 32 * hf + 64 * q + NH, a) + DECOMP_OFFSET;
                     }
                 }
-#pragma unroll 1
                 WSP(1);
+#pragma unroll 1
                 for (int p = 0; p < BK_L; p++) {
                     // ---- BSK producer duty (claimed in order by whichever front warp gets here first)
                     if (lane == 0) {
