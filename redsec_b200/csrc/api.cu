@@ -610,6 +610,17 @@ int rs_fp64_peak_three_operand(rs_ctx* ctx, double* tflops) {
     return RS_OK;
 }
 
+#ifdef RS_ERR_STATS
+int rs_debug_err_stats(unsigned long long* hist8, double* max_err) {   // debug builds only
+    cudaDeviceSynchronize();
+    unsigned long long bits = 0;
+    if (cudaMemcpyFromSymbol(hist8, rs::g_err_hist, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(&bits, rs::g_err_max_bits, sizeof(bits)) != cudaSuccess) return 1;
+    memcpy(max_err, &bits, sizeof(double));
+    return 0;
+}
+#endif
+
 #ifdef RS_WS_PROF
 int rs_debug_ws_prof(long long* out96) {   // debug builds only: phase timers of CTA 0, [12 warps][8 phases]
     cudaDeviceSynchronize();

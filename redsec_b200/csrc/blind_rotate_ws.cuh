@@ -42,6 +42,21 @@ __device__ long long g_ws_prof[12][8];
 #define WSP_FLUSH() do { } while (0)
 #endif
 
+#ifdef RS_ERR_STATS
+// pre-rounding error of the FFT external product (debug builds only: RS_NVCC_EXTRA=-DRS_ERR_STATS, scripts/phase_error.py):
+// histogram of |x - rint(x)| over every inverse-transform output, bins [0,1e-6) [1e-6,1e-5) ... [1e-2,1e-1) [1e-1,0.5], and the maximum
+__device__ unsigned long long g_err_hist[8];
+__device__ unsigned long long g_err_max_bits;
+__device__ __forceinline__ void err_stat(double x) {
+    const double e = fabs(x - rint(x));
+    const int bin = e < 1e-6 ? 0 : e < 1e-5 ? 1 : e < 1e-4 ? 2 : e < 1e-3 ? 3 : e < 1e-2 ? 4 : e < 1e-1 ? 5 : 6;
+    atomicAdd(&g_err_hist[bin], 1ull);
+    atomicMax(&g_err_max_bits, (unsigned long long)__double_as_longlong(e));
+}
+#else
+__device__ __forceinline__ void err_stat(double) {}
+#endif
+
 template <int STAGES, int XSLOTS>
 struct WsSmem {
     static constexpr int kCts = 4;
@@ -317,6 +332,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             }
 #pragma unroll
             for (int q = 0; q < 8; q++) {
+                err_stat(v[q].x); err_stat(v[q].y);
                 acc[poly * N + u + 64 * q] += (uint32_t)__double2ll_rn(v[q].x);
                 acc[poly * N + u + 64 * q + NH] += (uint32_t)__double2ll_rn(v[q].y);
             }
