@@ -176,6 +176,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when the environment
+        # sets NCCL_DEBUG) goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
