@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -45,6 +47,11 @@ struct rs_ctx {
     uint32_t* lin = nullptr; size_t lin_cap = 0;        // gate pre-combination
     uint32_t* wire = nullptr; size_t wire_cap = 0;      // wire-format staging (host variants)
     uint32_t* io0 = nullptr; uint32_t* io1 = nullptr; size_t io_cap = 0;
+    // caching allocator behind rs_lwe_alloc / rs_dev_alloc: layer forward allocates and frees an activation batch per layer,
+    // and cudaMalloc / cudaFree (a device-wide sync each) cost ~0.5 s per CIFAR image; freed blocks are kept and handed out
+    // again by size class.  All work is ordered on ctx->stream, so reuse right after a free is stream-safe.
+    std::multimap<size_t, void*> free_blocks;        // capacity -> block
+    std::unordered_map<void*, size_t> live_blocks;   // block -> capacity
     // measurement
     bool profiling = false;
     std::vector<ProfEvent> events;
@@ -92,6 +99,38 @@ struct LaunchScope {   // brackets one kernel launch with events when profiling 
         ctx->events.push_back(ev);
     }
 };
+
+int pool_alloc(rs_ctx* ctx, size_t bytes, void** out) {
+    const size_t want = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+    auto it = ctx->free_blocks.lower_bound(want);
+    if (it != ctx->free_blocks.end() && it->first <= want + want / 4 + 4096) {     // close enough in size: reuse
+        *out = it->second;
+        ctx->live_blocks[it->second] = it->first;
+        ctx->free_blocks.erase(it);
+        return RS_OK;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {      // out of memory: drop the cache and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+        ctx->free_blocks.clear();
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) return fail(ctx, RS_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    ctx->live_blocks[p] = want;
+    *out = p;
+    return RS_OK;
+}
+int pool_free(rs_ctx* ctx, void* p) {
+    if (!p) return RS_OK;
+    auto it = ctx->live_blocks.find(p);
+    if (it == ctx->live_blocks.end()) return fail(ctx, RS_ERR_ARG, "free of a pointer this context did not allocate");
+    ctx->free_blocks.emplace(it->second, p);
+    ctx->live_blocks.erase(it);
+    return RS_OK;
+}
 
 int grow(rs_ctx* ctx, uint32_t** p, size_t* cap, size_t words) {
     if (*cap >= words) return RS_OK;
@@ -265,6 +304,8 @@ int rs_ctx_destroy(rs_ctx* ctx) {
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
     cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->ksk7); cudaFree(ctx->ext); cudaFree(ctx->lin); cudaFree(ctx->wire);
     cudaFree(ctx->io0); cudaFree(ctx->io1);
+    for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+    for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RS_OK;
@@ -333,13 +374,11 @@ int rs_load_eval_key(rs_ctx* ctx, const uint32_t* bsk_host, const uint32_t* ksk_
 int rs_lwe_alloc(rs_ctx* ctx, size_t count, uint32_t** dev_out) {
     if (!ctx || !dev_out) return fail(ctx, RS_ERR_ARG, "rs_lwe_alloc: NULL argument");
     RS_CUDA(ctx, cudaSetDevice(ctx->device));
-    RS_CUDA(ctx, cudaMalloc(dev_out, (count ? count : 1) * rs::LWE_STRIDE * sizeof(uint32_t)));
-    return RS_OK;
+    return pool_alloc(ctx, (count ? count : 1) * rs::LWE_STRIDE * sizeof(uint32_t), reinterpret_cast<void**>(dev_out));
 }
 int rs_lwe_free(rs_ctx* ctx, uint32_t* dev) {
     if (!ctx) return RS_ERR_ARG;
-    RS_CUDA(ctx, cudaFree(dev));
-    return RS_OK;
+    return pool_free(ctx, dev);
 }
 int rs_lwe_upload(rs_ctx* ctx, uint32_t* dev, const uint32_t* host_wire, size_t count) {
     if (!ctx || !dev || !host_wire) return fail(ctx, RS_ERR_ARG, "rs_lwe_upload: NULL argument");
@@ -382,8 +421,7 @@ int rs_keyswitch_batch(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* ext_dev, 
 }
 int rs_ext_alloc(rs_ctx* ctx, size_t count, uint32_t** dev_out) {
     if (!ctx || !dev_out) return fail(ctx, RS_ERR_ARG, "rs_ext_alloc: NULL argument");
-    RS_CUDA(ctx, cudaMalloc(dev_out, (count ? count : 1) * rs::EXT_STRIDE * sizeof(uint32_t)));
-    return RS_OK;
+    return pool_alloc(ctx, (count ? count : 1) * rs::EXT_STRIDE * sizeof(uint32_t), reinterpret_cast<void**>(dev_out));
 }
 int rs_ext_upload(rs_ctx* ctx, uint32_t* dev, const uint32_t* host, size_t count) {
     if (!ctx || !dev || !host) return fail(ctx, RS_ERR_ARG, "rs_ext_upload: NULL argument");
@@ -507,13 +545,11 @@ int rs_lwe_interleave(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* gathered_d
 int rs_dev_alloc(rs_ctx* ctx, size_t bytes, void** dev_out) {
     if (!ctx || !dev_out) return fail(ctx, RS_ERR_ARG, "rs_dev_alloc: NULL argument");
     RS_CUDA(ctx, cudaSetDevice(ctx->device));
-    RS_CUDA(ctx, cudaMalloc(dev_out, bytes ? bytes : 1));
-    return RS_OK;
+    return pool_alloc(ctx, bytes, dev_out);
 }
 int rs_dev_free(rs_ctx* ctx, void* dev) {
     if (!ctx) return RS_ERR_ARG;
-    RS_CUDA(ctx, cudaFree(dev));
-    return RS_OK;
+    return pool_free(ctx, dev);
 }
 int rs_dev_upload(rs_ctx* ctx, void* dev, const void* host, size_t bytes) {
     if (!ctx || !dev || !host) return fail(ctx, RS_ERR_ARG, "rs_dev_upload: NULL argument");
