@@ -76,6 +76,14 @@ int rs_host_free(void *p);
  * redsec_binarize_bootstrap / redsec_unbinarize_bootstrap (lib/GPU/gates.cu:124-144), one call per layer
  * instead of one per neuron.  in == out is allowed. */
 int rs_pbs_batch(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *in_dev, size_t count, uint32_t mu);
+/* rs_pbs_lut_batch: programmable bootstrap with caller-supplied test vectors, lut_dev = uint32[lut_mod][1024] on the
+ * device; ciphertext c uses row c % lut_mod (rows are channel-fastest, so lut_mod = channels gives one table per channel):
+ *   out[c] = LWE(+lut[j]) if phase(in[c]) rounds to j/2048 in [0,1/2), LWE(-lut[j-1024]) in [1/2,1).
+ * The correct encrypted form of the DoReFa ReLU (multiply by slope, add bias, shift, clamp) that
+ * {Int,Bin}Func::Quantize::relu_shift (lib/IntFunc.cpp:934-973, lib/BinFunc.cpp:1120-1162) attempts with
+ * multiply_pc_ints + binarize_int + bootsMUX (functionally broken in the reference): ONE bootstrap per neuron
+ * whose test vector is the per-channel staircase. */
+int rs_pbs_lut_batch(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *in_dev, size_t count, const uint32_t *lut_dev, int lut_mod);
 /* rs_gate_batch: out[c] = boot((0,fix) +/- in0[c] +/- in1[c], mu); replaces bootsNAND..bootsXNOR
  * (lib/GPU/gates.cu:246-286) and BinOps::max -> bootsOR (lib/BinOps_enc.cpp:164-167). */
 int rs_gate_batch(rs_ctx *ctx, int gate, uint32_t *out_dev, const uint32_t *in0_dev, const uint32_t *in1_dev,
@@ -117,6 +125,8 @@ typedef struct rs_conv_desc {
 } rs_conv_desc;
 int rs_lwe_conv(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *in_dev, const int8_t *wpacked_dev,
                 const uint32_t *bias_dev /* [out_dep] torus32, may be NULL */, const rs_conv_desc *desc);
+/* dev[c].b += value for every row (adds the trivial sample (0,value)); lweNoiselessTrivial + lweAddTo, lib/BinOps_enc.cpp:137-141 */
+int rs_lwe_add_const(rs_ctx *ctx, uint32_t *dev, size_t count, uint32_t value);
 int rs_dev_alloc(rs_ctx *ctx, size_t bytes, void **dev_out);
 int rs_dev_free(rs_ctx *ctx, void *dev);
 int rs_dev_upload(rs_ctx *ctx, void *dev, const void *host, size_t bytes);
@@ -157,6 +167,9 @@ void rs_net_destroy(rs_net *net);
 int rs_net_add_layer(rs_net *net, int int_layer, int conv_type, int out_depth, int pool_type, int quant_type,
                      const rs_layer_params *p);
 int rs_net_prep(rs_net *net, const char *weights_path /* var_prep.dat */, int in_h, int in_w, int in_dep);
+/* same with the input tDimensions of the generated net spelled out (lay_dim.in_bits / up_bound / scale,
+ * nets/mnist/relu1024x1/net.cpp:96-110: 2, 2, 1); rs_net_prep uses the sign nets' 9, 510, 255 */
+int rs_net_prep_ex(rs_net *net, const char *weights_path, int in_h, int in_w, int in_dep, int in_bits, int up_bound, float scale);
 int rs_net_num_layers(const rs_net *net);
 int rs_net_layer_info(rs_net *net, int layer, size_t *out_count, int *channels, size_t *bootstraps, int *out_h, int *out_w);
 /* forward of one layer for rank's output-channel slice (world=1: whole layer).  Does not free in_dev; the caller

@@ -11,7 +11,8 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX=/usr/bin/g++
 LIBSRC="BinFunc.cpp BinLayer.cpp BinOps.cpp IntFunc.cpp IntLayer.cpp IntOps.cpp Layer.cpp"
-for net in mnist/sign1024x1 mnist/sign1024x2 mnist/sign1024x3 cifar/binarynet cifar/binarynet_small; do
+for net in mnist/sign1024x1 mnist/sign1024x2 mnist/sign1024x3 cifar/binarynet cifar/binarynet_small \
+           mnist/relu1024x1 mnist/relu1024x2 mnist/relu1024x3; do
   name=$(echo $net | tr '/' '_')
   [ -x "$OUT/ptxt_$name" ] && [ "$OUT/ptxt_$name" -nt "$HERE/ref_harness.cpp" ] && continue
   srcs=""; for f in $LIBSRC; do srcs="$srcs $REF/lib/$f"; done

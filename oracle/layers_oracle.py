@@ -7,6 +7,10 @@ Follows the reference loops, not the product's kernels:
   * sign activation + bias  lib/BinFunc.cpp:1044-1075, lib/IntFunc.cpp:860-889; plaintext binarize lib/BinOps.cpp:207-217
   * max pooling             lib/BinFunc.cpp:880-925 (as an OR tree at +-1/8, SURVEY.md H2 / defect R3)
   * layer sequencing        lib/BinLayer.cpp:150-241, lib/IntLayer.cpp:153-235
+  * DoReFa ReLU (row f4)    lib/IntFunc.cpp:934-973 plaintext branch: (slope*x + bias) >> slope_bits, clamp to [0, 2^shift_bits);
+                            slope_bits from lib/IntFunc.cpp:812-815; plaintext IntFunc conv: weight -1 contributes ~x = -x-1
+                            (IntOps::invert, lib/IntOps.cpp:72-82), zero weight contributes 0 (lib/IntFunc.cpp:270).
+                            Encrypted form = ONE test-vector bootstrap per neuron (relu_test_vectors below).
 The plaintext path is pinned against the reference's own plaintext build (oracle/_ref, golden scores in
 tests/golden/ptxt_scores.json).  The encrypted path is "parity unpinned" like the rest of the oracle (no TFHE here).
 A net spec is plain data (see redsec_b200/netspec.py); it is passed in by the caller, this module imports nothing
@@ -57,6 +61,8 @@ def prepare(spec: dict, weights_path: str):
     buf = memoryview(open(weights_path, "rb").read())
     pos = 0
     h, w, dep = spec["input"]
+    scale = float(spec.get("input_scale", 255))           # tDimensions.scale (nets/*/net.cpp "lay_dim.scale")
+    twin_conv = any(ls["act"] == "relu" for ls in spec["layers"])   # ReLU nets follow the plaintext twin's IntFunc conv
     layers = []
     for ls in spec["layers"]:
         L = PreparedLayer()
@@ -96,10 +102,24 @@ def prepare(spec: dict, weights_path: str):
                 oh, ow = (h - ph_ // 2 - 1) // sh + 1, (w - pw_ // 2 - 1) // sw + 1
             L.sp_geom = (ph_, pw_, sh, sw, ofh, ofw, oh, ow)
             h, w = oh, ow
+            scale *= ph_ * pw_                              # lib/IntFunc.cpp:629
         L.q_dims = (h, w, dep)
         L.bias, pos = _read_ints(buf, pos, dep)
-        if ls["act"] == "relu" and ls.get("e_bias") == 2:
-            _, pos = _read_ints(buf, pos, dep)
+        L.twin_conv = twin_conv and ls["kind"] == "int" and L.has_conv
+        if L.twin_conv:
+            L.neg_count = (L.weights == -1).sum(axis=(0, 1, 2)).astype(np.int64)   # per output channel
+        L.slope = None
+        if ls["act"] == "relu":
+            L.shift_bits = ls["shift_bits"]
+            if ls.get("e_bias") == 2 and L.shift_bits > 1:
+                L.slope, pos = _read_ints(buf, pos, dep)
+            sc_b = 0
+            while (1 << sc_b) < scale:
+                sc_b += 1
+            L.slope_bits = 8 + sc_b - L.shift_bits           # SLOPE_BITS=8 (lib/IntFunc.cpp:45,815)
+            scale = float((1 << L.shift_bits) - 1)           # lib/IntFunc.cpp:836-837
+        elif ls["act"] == "sign":
+            scale = 1.0
         L.has_maxpool = ls["pool"] == "max" and ls["act"] == "sign" and conv != "fc_final"
         if L.has_maxpool:
             ph_, pw_ = ls["pool_win"]
@@ -184,14 +204,27 @@ def plain_forward(layers, pixels, enc_conv_semantics=False, collect=None):
             x = x.reshape((L.sp_in if L.has_sumpool else L.q_dims[:2]) + (L.q_dims[2],))
         if L.has_conv:
             x = x.reshape(L.cin)
-            int_mode = ls["kind"] == "int" and enc_conv_semantics
+            int_mode = ls["kind"] == "int" and enc_conv_semantics and not L.twin_conv
             term = np.int64(-1) if int_mode else None
             x = _conv(L, x, term, term)
+            if L.twin_conv:
+                x = x - L.neg_count                       # weight -1 contributes ~x = -x - 1
         if L.has_sumpool:
             x = _sumpool(L, x)
+        if ls["act"] == "relu":
+            x = relu_shift(L, x)
+            if collect is not None:
+                collect.append(x.copy())
+            x = x.reshape(-1)
+            continue
         x = x + L.bias.astype(np.int64)
         if ls["act"] == "none":
-            return x.reshape(-1)
+            if L is layers[-1]:
+                return x.reshape(-1)
+            if collect is not None:
+                collect.append(x.copy())
+            x = x.reshape(-1)
+            continue
         x = (x >= 0).astype(np.int64)                    # binarize: val<0 -> 0 else 1
         if L.has_maxpool:
             ph_, pw_, sh, sw, oh, ow = L.mp_geom
@@ -204,6 +237,42 @@ def plain_forward(layers, pixels, enc_conv_semantics=False, collect=None):
             collect.append(x.copy())
         x = x.reshape(-1)
     return x
+
+
+def relu_shift(L, x):
+    """Plaintext DoReFa ReLU of lib/IntFunc.cpp:964-967 on integers x[..., channel]."""
+    x = np.asarray(x, dtype=np.int64)
+    slope = L.slope.astype(np.int64) if L.slope is not None else np.ones(x.shape[-1], dtype=np.int64)
+    v = (x * slope + L.bias.astype(np.int64)) >> L.slope_bits          # IntOps::shift: arithmetic >>
+    return np.clip(v, 0, (1 << L.shift_bits) - 1)                       # IntOps::relu
+
+
+def relu_test_vectors(L):
+    """Per-channel test vectors [dep][1024] (torus32) of the encrypted ReLU: the neuron value x sits on the torus in units
+    of 1/4096, a bootstrap resolves 2N = 2048 phase slots, so slot j <-> x = 2j.  The staircase f saturates on both sides, so
+    g = f - (2^shift_bits - 1)/2 is made negacyclic: slots [0,512) hold g(2j) (small positive x; large negative x sees
+    -g = saturated value), slots [512,1024) hold -g(2j - 2048) (small negative x).  The caller adds the constant
+    (2^shift_bits - 1)/2 back after the bootstrap."""
+    dep = L.q_dims[2]
+    half = ((1 << L.shift_bits) - 1) * (UNIT // 2)
+    j = np.arange(1024, dtype=np.int64)
+    xs = np.where(j < 512, 2 * j, 2 * j - 2048)                         # [1024]
+    f = relu_shift(L, np.broadcast_to(xs[:, None], (1024, dep)))        # [1024][dep]
+    g = f * UNIT - half
+    tv = np.where((j < 512)[:, None], g, -g)
+    return np.ascontiguousarray((tv.T & 0xFFFFFFFF).astype(np.uint32)), half
+
+
+def predicted_lut_message(ct, luts, lwe_key):
+    """What a test-vector bootstrap of ct[c] with luts[c % m] must decrypt to (torus32, before output noise): the blind rotation
+    ends at slot (barb - sum bara_i s_i) mod 2N, slots [N,2N) read the negated table."""
+    ct = np.ascontiguousarray(ct, dtype=np.uint32).reshape(-1, O.LWE_WORDS)
+    luts = np.ascontiguousarray(luts, dtype=np.uint32).reshape(-1, O.N)
+    bar = (((ct.astype(np.uint64) << np.uint64(32)) + np.uint64(1 << 52)) >> np.uint64(53)).astype(np.int64) % (2 * O.N)  # round to 2N
+    slot = (bar[:, O.n] - bar[:, :O.n] @ np.asarray(lwe_key, dtype=np.int64)) % (2 * O.N)
+    rows = np.arange(ct.shape[0]) % luts.shape[0]
+    v = luts[rows, slot % O.N].astype(np.int64)
+    return np.where(slot < O.N, v, -v) & 0xFFFFFFFF, slot
 
 
 def plain_layer_preact(L, x_in):
@@ -242,16 +311,19 @@ def enc_linear(L, ct):
     if L.has_conv:
         x = x.reshape(L.cin + (O.LWE_WORDS,))
         term = None
-        if ls["kind"] == "int":                         # trivial sample (0, -1/4096)
+        if ls["kind"] == "int" and not L.twin_conv:     # trivial sample (0, -1/4096)
             term = np.zeros(O.LWE_WORDS, dtype=np.uint32)
             term[O.n] = (-UNIT) & 0xFFFFFFFF
         x = _conv(L, x, term, term)
+        if L.twin_conv:                                 # plaintext-twin IntFunc conv: weight -1 contributes -x - 1
+            x[..., O.n] -= (L.neg_count * UNIT & 0xFFFFFFFF).astype(np.uint32)[None, None, :]
     if L.has_sumpool:
         if not L.has_conv:
             x = x.reshape(L.sp_in + (L.q_dims[2], O.LWE_WORDS))
         x = _sumpool(L, x)
     x = x.reshape(L.q_dims + (O.LWE_WORDS,)).copy()
-    x[..., O.n] += (L.bias.astype(np.int64) * UNIT & 0xFFFFFFFF).astype(np.uint32)[None, None, :]
+    if ls["act"] != "relu":                             # the ReLU bias lives inside the test vector (slope*x + bias)
+        x[..., O.n] += (L.bias.astype(np.int64) * UNIT & 0xFFFFFFFF).astype(np.uint32)[None, None, :]
     return x.reshape(-1, O.LWE_WORDS)
 
 
@@ -260,6 +332,11 @@ def enc_layer_forward(L, ct, ks, threads=0):
     lin = enc_linear(L, ct)
     if L.spec["act"] == "none":
         return lin
+    if L.spec["act"] == "relu":                         # ONE test-vector bootstrap per neuron, then + (2^shift_bits-1)/2
+        tv, half = relu_test_vectors(L)
+        out = O.pbs_lut(lin, tv, ks, threads=threads)
+        out[:, O.n] += np.uint32(half)
+        return out
     if not L.has_maxpool:
         return O.pbs(lin, UNIT, ks, threads=threads)
     bits = O.pbs(lin, EIGHTH, ks, threads=threads).reshape(L.q_dims + (O.LWE_WORDS,))
@@ -293,7 +370,7 @@ def encode_pixels(pixels):
 def count_bootstraps(layers):
     n = 0
     for L in layers:
-        if L.spec["act"] != "sign":
+        if L.spec["act"] not in ("sign", "relu"):
             continue
         h, w, d = L.q_dims
         n += h * w * d

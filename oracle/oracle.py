@@ -147,6 +147,16 @@ def pbs(ct, mu: int, ks: KeySet, exact: bool = False, threads: int = 0, stats=No
     return out
 
 
+def pbs_lut(ct, luts, ks: KeySet, exact: bool = False, threads: int = 0):
+    """Programmable bootstrap with per-ciphertext test vectors: ciphertext c uses luts[c % len(luts)] (row f4)."""
+    ct = np.ascontiguousarray(ct, dtype=np.uint32).reshape(-1, LWE_WORDS)
+    luts = np.ascontiguousarray(luts, dtype=np.uint32).reshape(-1, N)
+    out = np.empty_like(ct)
+    lib().orc_pbs_lut_batch(_p(out), _p(ct), C.c_int(ct.shape[0]), _p(luts), C.c_int(luts.shape[0]), _p(ks.bsk),
+                            _p(ks.bsk_fft, C.c_double), _p(ks.ksk), C.c_int(int(exact)), C.c_int(threads))
+    return out
+
+
 def gate_linear(op: str, a, b):
     a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, LWE_WORDS)
     b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, LWE_WORDS)

@@ -226,19 +226,21 @@ static inline int32_t decomp_digit(uint32_t v_plus_offset, int p /*0-based*/) {
     int decal = 32 - (p + 1) * ORC_BGBIT;
     return (int32_t)((v_plus_offset >> decal) & 7u) - 4;
 }
-static void init_acc(uint32_t *acc, int *bara, const uint32_t *lwe_in, uint32_t mu) {
+/* tv == NULL: the constant test vector mu*(1+X+...+X^(N-1)) of tfhe_bootstrap_FFT; otherwise a caller-supplied
+ * test vector (programmable bootstrap: coefficient j is the output for a phase that rounds to j/2N) */
+static void init_acc(uint32_t *acc, int *bara, const uint32_t *lwe_in, uint32_t mu, const uint32_t *tv_in) {
     int barb = orc_modswitch_from_torus32(lwe_in[n_], 2 * N_);
     for (int i = 0; i < n_; i++) bara[i] = orc_modswitch_from_torus32(lwe_in[i], 2 * N_) % (2 * N_);
     barb %= 2 * N_;
     uint32_t tv[N_];
-    for (int j = 0; j < N_; j++) tv[j] = mu;
+    for (int j = 0; j < N_; j++) tv[j] = tv_in ? tv_in[j] : mu;
     memset(acc, 0, N_ * sizeof(uint32_t));
     poly_mul_by_xai(acc + N_, (2 * N_ - barb) % (2 * N_), tv);
 }
 
-void orc_blind_rotate_exact(uint32_t *acc, const uint32_t *lwe_in, uint32_t mu, const uint32_t *bsk) {
+static void blind_rotate_exact_tv(uint32_t *acc, const uint32_t *lwe_in, uint32_t mu, const uint32_t *tv, const uint32_t *bsk) {
     int bara[n_];
-    init_acc(acc, bara, lwe_in, mu);
+    init_acc(acc, bara, lwe_in, mu, tv);
     const uint32_t off = decomp_offset();
     uint32_t *tmp = (uint32_t *)malloc(2 * N_ * sizeof(uint32_t));
     uint32_t *ext = (uint32_t *)malloc(2 * N_ * sizeof(uint32_t));
@@ -271,10 +273,19 @@ void orc_blind_rotate_exact(uint32_t *acc, const uint32_t *lwe_in, uint32_t mu, 
     free(tmp); free(ext); free(res);
 }
 
+void orc_blind_rotate_exact(uint32_t *acc, const uint32_t *lwe_in, uint32_t mu, const uint32_t *bsk) {
+    blind_rotate_exact_tv(acc, lwe_in, mu, NULL, bsk);
+}
+static void blind_rotate_fft_tv(uint32_t *acc, const uint32_t *lwe_in, uint32_t mu, const uint32_t *tv, const double *bsk_fft,
+                                double *err_stats);
 void orc_blind_rotate_fft(uint32_t *acc, const uint32_t *lwe_in, uint32_t mu, const double *bsk_fft, double *err_stats) {
+    blind_rotate_fft_tv(acc, lwe_in, mu, NULL, bsk_fft, err_stats);
+}
+static void blind_rotate_fft_tv(uint32_t *acc, const uint32_t *lwe_in, uint32_t mu, const uint32_t *tv, const double *bsk_fft,
+                                double *err_stats) {
     fft_init();
     int bara[n_];
-    init_acc(acc, bara, lwe_in, mu);
+    init_acc(acc, bara, lwe_in, mu, tv);
     const uint32_t off = decomp_offset();
     uint32_t tmp[2 * N_];
     int32_t dig[N_];
@@ -363,6 +374,27 @@ void orc_pbs_batch(uint32_t *out, const uint32_t *in, int count, uint32_t mu, co
         if (st[0] > emax) emax = st[0]; esum += st[1]; ecnt += st[2];
     }
     if (err_stats) { if (emax > err_stats[0]) err_stats[0] = emax; err_stats[1] += esum; err_stats[2] += ecnt; }
+}
+
+/* programmable bootstrap with caller-supplied test vectors: ciphertext c uses luts[(c % lut_mod)][N]; the output is
+ * LWE(tv[j]) for a phase that rounds to j/2N in [0,1/2) and LWE(-tv[j-N]) in [1/2,1).  This is the correct encrypted
+ * form of the DoReFa ReLU staircase of lib/IntFunc.cpp:934-973 (defect R6). */
+void orc_pbs_lut_batch(uint32_t *out, const uint32_t *in, int count, const uint32_t *luts, int lut_mod, const uint32_t *bsk,
+                       const double *bsk_fft, const uint32_t *ksk, int exact, int threads) {
+    fft_init();
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#endif
+    #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (int c = 0; c < count; c++) {
+        uint32_t acc[2 * N_], ext[N_ + 1], res[ORC_LWE_WORDS];
+        const uint32_t *tv = luts + (size_t)(c % lut_mod) * N_;
+        if (exact) blind_rotate_exact_tv(acc, in + (size_t)c * ORC_LWE_WORDS, 0, tv, bsk);
+        else blind_rotate_fft_tv(acc, in + (size_t)c * ORC_LWE_WORDS, 0, tv, bsk_fft, NULL);
+        orc_sample_extract(ext, acc);
+        orc_keyswitch(res, ext, ksk);
+        memcpy(out + (size_t)c * ORC_LWE_WORDS, res, sizeof(res));
+    }
 }
 
 /* ------------------------------------------------------------------ gates (A.3) */

@@ -75,6 +75,11 @@ void orc_pbs_batch(uint32_t *out, const uint32_t *in, int count, uint32_t mu,
                    const uint32_t *bsk, const double *bsk_fft, const uint32_t *ksk, int exact, int threads,
                    double *err_stats);
 
+/* programmable bootstrap with per-ciphertext test vectors luts[lut_mod][N] (ciphertext c uses row c % lut_mod):
+ * the correct encrypted form of the DoReFa ReLU of lib/IntFunc.cpp:934-973 (row f4) */
+void orc_pbs_lut_batch(uint32_t *out, const uint32_t *in, int count, const uint32_t *luts, int lut_mod,
+                       const uint32_t *bsk, const double *bsk_fft, const uint32_t *ksk, int exact, int threads);
+
 /* gate linear part (lib/GPU/gates.cu:44-108): out = (0,fix) +/- in0 +/- in1 (x2 for XOR/XNOR) */
 void orc_gate_linear(int op, uint32_t *out, const uint32_t *in0, const uint32_t *in1, int count);
 void orc_gate_batch(int op, uint32_t *out, const uint32_t *in0, const uint32_t *in1, int count, uint32_t mu,

@@ -27,6 +27,7 @@ SIGNATURES = {
     "rs_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
     "rs_host_free": (C.c_int, [vp]),
     "rs_pbs_batch": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_uint32]),
+    "rs_pbs_lut_batch": (C.c_int, [vp, vp, vp, C.c_size_t, vp, C.c_int]),
     "rs_gate_batch": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_uint32]),
     "rs_pbs_batch_host": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_uint32]),
     "rs_gate_batch_host": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_uint32]),
@@ -36,6 +37,7 @@ SIGNATURES = {
     "rs_ext_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "rs_ext_download": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "rs_lwe_lincomb": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, vp, vp]),
+    "rs_lwe_add_const": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32]),
     "rs_dev_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "rs_dev_free": (C.c_int, [vp, vp]),
     "rs_dev_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
@@ -59,6 +61,7 @@ SIGNATURES = {
     "rs_net_destroy": (None, [vp]),
     "rs_net_add_layer": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "rs_net_prep": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "rs_net_prep_ex": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "rs_net_num_layers": (C.c_int, [vp]),
     "rs_net_layer_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rs_net_layer_forward": (C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -150,8 +150,8 @@ int grow(rs_ctx* ctx, uint32_t** p, size_t* cap, size_t words) {
 // variant 4 = variant 3 with a 4-stage smem ring.
 struct BrVariant { int groups, stages, smem; void (*set_attr)(cudaError_t*); };
 template <int G, int S>
-void br_launch(rs_ctx* ctx, int grid, const uint32_t* in, int count, uint32_t mu, uint32_t* ext) {
-    rs::blind_rotate_kernel<G, S><<<grid, G * 64, rs::BrSmem<G, S>::kTotal, ctx->stream>>>(in, count, mu, ctx->bsk_f, ext);
+void br_launch(rs_ctx* ctx, int grid, const uint32_t* in, int count, uint32_t mu, uint32_t* ext, const uint32_t* lut, int lut_mod) {
+    rs::blind_rotate_kernel<G, S><<<grid, G * 64, rs::BrSmem<G, S>::kTotal, ctx->stream>>>(in, count, mu, ctx->bsk_f, ext, lut, lut_mod);
 }
 template <int G, int S>
 cudaError_t br_prepare() {
@@ -162,9 +162,12 @@ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 constexpr int kMaxSmemNeeded = cmax(cmax(rs::BrSmem<4, 7>::kTotal, rs::WsSmem<kWsStages, kWsSlots>::kTotal),
                                     cmax(rs::TmSmem<5, 3>::kTotal, rs::TmSmem<5, 3>::kTotal));
 
-int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t count, uint32_t mu) {
+int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t count, uint32_t mu,
+                        const uint32_t* lut = nullptr, int lut_mod = 1) {
     if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
     if (count == 0) return RS_OK;
+    if (lut && (ctx->br_variant == 3 || ctx->br_variant == 4))
+        return fail(ctx, RS_ERR_STATE, "test-vector bootstraps are not implemented in the tensor-memory variants (rs_set_tuning 3/4)");
     constexpr int G = 4;
     const int grid = (int)((count + G - 1) / G);
     // warp-specialised kernels partition the batch evenly over the grid; a batch below one wave (the 196-neuron MNIST layer)
@@ -179,9 +182,9 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
             rs::blind_rotate_tm_kernel<4, 3, 120, 184><<<grid, 512, rs::TmSmem<5, 3>::kTotal, ctx->stream>>>(in, (int)count, mu, ctx->bsk_f, ext);
         else if (ctx->br_variant == 0)
             rs::blind_rotate_ws_kernel<kWsStages, kWsSlots><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
-                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep);
-        else if (ctx->br_variant == 1) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext);
-        else br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext);
+                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);
+        else if (ctx->br_variant == 1) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext, lut, lut_mod);
+        else br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext, lut, lut_mod);
     }
     RS_CUDA(ctx, cudaGetLastError());
     return RS_OK;
@@ -444,6 +447,14 @@ int rs_pbs_batch(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* in_dev, size_t 
     return launch_keyswitch(ctx, out_dev, ctx->ext, count);
 }
 
+int rs_pbs_lut_batch(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* in_dev, size_t count, const uint32_t* lut_dev, int lut_mod) {
+    if (!ctx || !out_dev || !in_dev || !lut_dev) return fail(ctx, RS_ERR_ARG, "rs_pbs_lut_batch: NULL argument");
+    if (lut_mod < 1) return fail(ctx, RS_ERR_ARG, "rs_pbs_lut_batch: lut_mod %d < 1", lut_mod);
+    if (int r = grow(ctx, &ctx->ext, &ctx->ext_cap, count * rs::EXT_STRIDE)) return r;
+    if (int r = launch_blind_rotate(ctx, ctx->ext, in_dev, count, 0u, lut_dev, lut_mod)) return r;
+    return launch_keyswitch(ctx, out_dev, ctx->ext, count);
+}
+
 int rs_gate_batch(rs_ctx* ctx, int gate, uint32_t* out_dev, const uint32_t* in0_dev, const uint32_t* in1_dev, size_t count,
                   uint32_t mu) {
     if (!ctx || !out_dev || !in0_dev || !in1_dev) return fail(ctx, RS_ERR_ARG, "rs_gate_batch: NULL argument");
@@ -537,6 +548,17 @@ int rs_lwe_interleave(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* gathered_d
         LaunchScope ls(ctx, RS_K_LINEAR);
         rs::lwe_interleave_kernel<<<(unsigned)(rows < cap ? rows : cap), rs::LWE_STRIDE / 4, 0, ctx->stream>>>(
             reinterpret_cast<uint4*>(out_dev), reinterpret_cast<const uint4*>(gathered_dev), pixels, c_local, world);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_lwe_add_const(rs_ctx* ctx, uint32_t* dev, size_t count, uint32_t value) {
+    if (!ctx || !dev) return fail(ctx, RS_ERR_ARG, "rs_lwe_add_const: NULL argument");
+    if (count == 0) return RS_OK;
+    {
+        LaunchScope ls(ctx, RS_K_LINEAR);
+        rs::lwe_add_const_kernel<<<grid_for(ctx, count, 256), 256, 0, ctx->stream>>>(dev, count, value);
     }
     RS_CUDA(ctx, cudaGetLastError());
     return RS_OK;

@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(GROUPS * 64, 1)
 blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRIDE]
                     int count, uint32_t mu,
                     const double2* __restrict__ bsk_f,       // [n][BK_ROWS][2][NH]
-                    uint32_t* __restrict__ ext_out)          // [count][EXT_STRIDE]
+                    uint32_t* __restrict__ ext_out,          // [count][EXT_STRIDE]
+                    const uint32_t* __restrict__ lut,        // [lut_mod][N] test vectors (row c % lut_mod) or nullptr (constant mu)
+                    int lut_mod)
 {
     using S = BrSmem<GROUPS, STAGES>;
     constexpr int AHEAD = 2;                // a group starting row rc makes sure slabs <= rc+AHEAD have been requested
@@ -216,9 +218,12 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
     const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
     for (int i = t; i < LWE_N; i += 64) bara[i] = (uint16_t)modswitch_2N(lwe[i]);
     const int barb = (int)modswitch_2N(lwe[LWE_N]);
+    const uint32_t* tv = lut ? lut + (size_t)(ct % lut_mod) * N : nullptr;
     for (int j = t; j < N; j += 64) {
         acc[j] = 0;
-        acc[N + j] = (((j + barb) & (2 * N - 1)) < N) ? mu : 0u - mu;   // X^{2N-barb} * (mu + mu X + ...)
+        const int idx = (j + barb) & (2 * N - 1);                        // X^{2N-barb} * testvector
+        const uint32_t v = tv ? tv[idx & (N - 1)] : mu;                  // (mu + mu X + ... for the sign bootstrap)
+        acc[N + j] = idx < N ? v : 0u - v;
     }
     Twiddles tw;
     make_twiddles(tw, t);

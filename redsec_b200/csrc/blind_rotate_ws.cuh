@@ -88,7 +88,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                        int count, uint32_t mu,
                        const double2* __restrict__ bsk_f,       // [n][BK_ROWS][2][NH]
                        uint32_t* __restrict__ ext_out,          // [count][EXT_STRIDE]
-                       float l2_keep)                           // fraction of the BSK stream marked L2 evict_last (0 = no hint)
+                       float l2_keep,                           // fraction of the BSK stream marked L2 evict_last (0 = no hint)
+                       const uint32_t* __restrict__ lut,        // [lut_mod][N] test vectors (ciphertext c uses row c % lut_mod), or
+                       int lut_mod)                             // nullptr: the constant test vector mu of the sign bootstrap
 {
     using S = WsSmem<STAGES, XSLOTS>;
     constexpr int AHEAD = 1;                       // a front warp starting row r makes sure slabs <= r+AHEAD are requested
@@ -142,9 +144,12 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
         for (int i = lane; i < LWE_N; i += 32) bara[i] = (uint16_t)modswitch_2N(lwe[i]);
         const int barb = (int)modswitch_2N(lwe[LWE_N]);
+        const uint32_t* tv = lut ? lut + (size_t)(ct % lut_mod) * N : nullptr;
         for (int k = lane; k < N; k += 32) {
             acc[k] = 0;
-            acc[N + k] = (((k + barb) & (2 * N - 1)) < N) ? mu : 0u - mu;   // X^{2N-barb} * (mu + mu X + ...)
+            const int idx = (k + barb) & (2 * N - 1);                        // X^{2N-barb} * testvector
+            const uint32_t v = tv ? tv[idx & (N - 1)] : mu;                  // (mu + mu X + ... for the sign bootstrap)
+            acc[N + k] = idx < N ? v : 0u - v;
         }
         __syncwarp();
 

@@ -11,6 +11,10 @@
 // Max-pool (reference defect R3): the reference ORs +-1/4096 bits with a gate that expects +-1/8,
 // starting from an uninitialised accumulator (lib/BinFunc.cpp:891,917).  Here the sign bootstrap in front of a
 // max-pool emits +-1/8, the OR tree runs at +-1/8 and its last level emits +-1/4096 again.
+// DoReFa ReLU (lib/IntFunc.cpp:934-973): the reference's encrypted branch (multiply_pc_ints on a
+// never-cleared scratch + binarize + bootsMUX on non-gate encodings, defect R6) cannot work; the plaintext branch defines
+// out = clamp((slope*x + bias) >> slope_bits, 0, 2^shift_bits - 1).  Here that staircase is ONE test-vector bootstrap per
+// neuron (rs_pbs_lut_batch) with one table per output channel; see relu_tables().
 #include <cassert>
 #include <cmath>
 #include <cstdlib>
@@ -108,6 +112,14 @@ public:
     // quantize
     int q_h = 0, q_w = 0, q_dep = 0;    // dims at the activation
     std::vector<uint32_t> bias_torus;   // [q_dep]
+    // DoReFa ReLU (IntLayer only)
+    std::vector<int32_t> bias_int, slope;   // [q_dep]; slope empty = 1
+    int shift_bits = 0, slope_bits = 0;
+    // IntFunc conv conventions: false = the reference's ENCRYPTED branch (zero weight / padding contribute -1/4096,
+    // lib/IntFunc.cpp:268,277); true = its plaintext twin (weight -1 contributes ~x = -x-1, IntOps::invert
+    // lib/IntOps.cpp:72-82; zero weight 0), which is what the shipped ReLU weights were converted for
+    bool twin_conv = false;
+    std::vector<int32_t> neg_count;     // [cout_dep] number of -1 weights per output channel (twin_conv)
     // max-pool geometry
     bool has_maxpool = false;
     int mp_out_h = 0, mp_out_w = 0;
@@ -115,10 +127,14 @@ public:
     std::map<std::pair<int, int>, ConvWeights> conv_cache;
     std::map<std::pair<int, int>, std::unique_ptr<DevCsr>> sumpool_cache, identity_cache;
     std::map<int, std::unique_ptr<PoolPlan>> maxpool_cache;
+    std::map<std::pair<int, int>, void*> relu_cache;
 
     ~LayerImpl() {
         for (auto& kv : conv_cache) { rs_dev_free(ctx, kv.second.packed); rs_dev_free(ctx, kv.second.bias); }
+        for (auto& kv : relu_cache) rs_dev_free(ctx, kv.second);
     }
+    bool is_relu() const { return eq == E_ACTIVATION_RELU; }
+    bool conv_is_twin() const { return twin_conv && int_inputs && has_conv; }
 
     int channels() const { return q_dep; }
     size_t final_h() const { return has_maxpool ? mp_out_h : q_h; }
@@ -170,6 +186,9 @@ public:
             }
             const size_t K = (size_t)cv.window.h * cv.window.w * cin_dep;
             RS_TRY(read_ternary(fd, weights, K * cout_dep));
+            neg_count.assign(cout_dep, 0);
+            for (size_t k = 0; k < K; k++)
+                for (int od = 0; od < cout_dep; od++) neg_count[od] += weights[k * cout_dep + od] < 0;
             dim->up_bound *= (uint32_t)(dim->filter_bits * cv.window.w * cv.window.h) * dim->in_dep;
             for (dim->in_bits = dim->in_bits; (dim->up_bound >> dim->in_bits) > 0; dim->in_bits++) {}
             dim->hw.h = (int16_t)cout_h; dim->hw.w = (int16_t)cout_w; dim->in_dep = cout_dep;
@@ -193,13 +212,21 @@ public:
         }
         // quantize: bias block of length in_dep (lib/BinFunc.cpp:1001-1003)
         q_h = dim->hw.h; q_w = dim->hw.w; q_dep = (int)dim->in_dep;
-        std::vector<int32_t> bias;
-        RS_TRY(read_ints(fd, bias, (size_t)q_dep));
+        RS_TRY(read_ints(fd, bias_int, (size_t)q_dep));
         bias_torus.resize(q_dep);
-        for (int i = 0; i < q_dep; i++) bias_torus[i] = (uint32_t)bias[i] * kUnit;   // modSwitchToTorus32(b, 4096)
-        if (eq == E_ACTIVATION_RELU && np.e_bias == E_BNORM) {   // slope block is present in the file; f4 is out of scope
-            std::vector<int32_t> slope;
-            RS_TRY(read_ints(fd, slope, (size_t)q_dep));
+        for (int i = 0; i < q_dep; i++) bias_torus[i] = (uint32_t)bias_int[i] * kUnit;   // modSwitchToTorus32(b, 4096)
+        if (is_relu()) {   // lib/IntFunc.cpp:800-840
+            if (!int_inputs) return RS_ERR_STATE;   // BinFunc::Quantize::relu_shift (no shipped net uses it) is not built
+            shift_bits = np.quant.shift_bits;
+            if (shift_bits < 2 || shift_bits > 8) return RS_ERR_ARG;
+            if (np.e_bias == E_BNORM) RS_TRY(read_ints(fd, slope, (size_t)q_dep));   // slope block (IntLayer.cpp:96-100)
+            int sc_b = 0;
+            while ((float)(1 << sc_b) < dim->scale) sc_b++;                          // log2(scale), IntFunc.cpp:813-814
+            slope_bits = 8 + sc_b - shift_bits;                                      // SLOPE_BITS = 8 (IntFunc.cpp:45,815)
+            if (slope_bits < 0) return RS_ERR_ARG;
+            dim->in_bits = (uint8_t)shift_bits;
+            dim->scale = (float)((1 << shift_bits) - 1);
+            dim->up_bound = 1u << (shift_bits - 1);
         }
         if (eq == E_ACTIVATION_SIGN) { dim->in_bits = 1; dim->up_bound = 1; dim->scale = 1.0f; }
         dim->out_bits = SINGLE_BIT;
@@ -231,9 +258,17 @@ public:
             ConvWeights cw;
             RS_TRY(rs_dev_alloc(ctx, packed.size(), &cw.packed));
             RS_TRY(rs_dev_upload(ctx, cw.packed, packed.data(), packed.size()));
-            if (!has_sumpool) {   // bias rides on the conv when nothing linear follows it
+            // the layer bias rides on the conv when nothing linear follows it (a ReLU keeps its bias inside the test
+            // vector); the plaintext-twin convention adds -1 per negative weight
+            const bool layer_bias = !has_sumpool && !is_relu();
+            if (layer_bias || conv_is_twin()) {
+                std::vector<uint32_t> cb(cl, 0u);
+                for (int c = 0; c < cl; c++) {
+                    if (layer_bias) cb[c] = bias_torus[c0 + c];
+                    if (conv_is_twin()) cb[c] -= (uint32_t)neg_count[c0 + c] * kUnit;
+                }
                 RS_TRY(rs_dev_alloc(ctx, (size_t)cl * 4, &cw.bias));
-                RS_TRY(rs_dev_upload(ctx, cw.bias, bias_torus.data() + c0, (size_t)cl * 4));
+                RS_TRY(rs_dev_upload(ctx, cw.bias, cb.data(), (size_t)cl * 4));
             }
             it = conv_cache.emplace(key, cw).first;
         }
@@ -260,7 +295,7 @@ public:
                                 csr.entry(((ih0 + fh) * sp_in_w + iw0 + fw) * cl + c, 1);
                             }
                         }
-                        csr.end_row(bias_torus[c0 + c]);
+                        csr.end_row(is_relu() ? 0u : bias_torus[c0 + c]);
                     }
             auto dev = std::make_unique<DevCsr>();
             RS_TRY(dev->upload(ctx, csr));
@@ -277,12 +312,44 @@ public:
         if (it == identity_cache.end()) {
             Csr csr;
             for (int p = 0; p < q_h * q_w; p++)
-                for (int c = c0; c < c1; c++) { csr.entry(p * q_dep + c, 1); csr.end_row(bias_torus[c]); }
+                for (int c = c0; c < c1; c++) { csr.entry(p * q_dep + c, 1); csr.end_row(is_relu() ? 0u : bias_torus[c]); }
             auto dev = std::make_unique<DevCsr>();
             RS_TRY(dev->upload(ctx, csr));
             it = identity_cache.emplace(key, std::move(dev)).first;
         }
         *out = it->second.get();
+        return RS_OK;
+    }
+
+    // Test vectors of the encrypted DoReFa ReLU for channels [c0,c1): uint32[cl][1024] on the device.  The neuron value x
+    // sits on the torus in units of 1/4096 and a bootstrap resolves 2N = 2048 phase slots, so slot j <-> x = 2j.  The
+    // staircase f(x) = clamp((slope*x + bias) >> slope_bits, 0, 2^shift_bits - 1) saturates on both sides, so
+    // g = f - (2^shift_bits - 1)/2 extends negacyclically: slots [0,512) hold g(2j) (x in [0,1024); x in [-2048,-1024) reads
+    // -g there, the saturated value), slots [512,1024) hold -g(2j-2048) (x in [-1024,0)).  forward() adds the constant back.
+    uint32_t relu_half() const { return (uint32_t)((1 << shift_bits) - 1) * (kUnit / 2); }
+    int relu_tables(int c0, int c1, void** out) {
+        auto key = std::make_pair(c0, c1);
+        auto it = relu_cache.find(key);
+        if (it == relu_cache.end()) {
+            const int cl = c1 - c0;
+            std::vector<uint32_t> tv((size_t)cl * RS_TLWE_N);
+            const int64_t top = (1 << shift_bits) - 1;
+            for (int c = 0; c < cl; c++) {
+                const int64_t sl = slope.empty() ? 1 : slope[c0 + c], b = bias_int[c0 + c];
+                for (int j = 0; j < RS_TLWE_N; j++) {
+                    const int64_t x = j < RS_TLWE_N / 2 ? 2 * j : 2 * j - 2 * RS_TLWE_N;
+                    int64_t v = (sl * x + b) >> slope_bits;        // IntOps::shift: arithmetic shift (lib/IntOps.cpp:194)
+                    v = v < 0 ? 0 : (v > top ? top : v);           // IntOps::relu (lib/IntOps.cpp:152-171)
+                    const uint32_t g = (uint32_t)v * kUnit - relu_half();
+                    tv[(size_t)c * RS_TLWE_N + j] = j < RS_TLWE_N / 2 ? g : 0u - g;
+                }
+            }
+            void* dev = nullptr;
+            RS_TRY(rs_dev_alloc(ctx, tv.size() * 4, &dev));
+            RS_TRY(rs_dev_upload(ctx, dev, tv.data(), tv.size() * 4));
+            it = relu_cache.emplace(key, dev).first;
+        }
+        *out = it->second;
         return RS_OK;
     }
 
@@ -363,7 +430,6 @@ public:
     // ---- forward for the channel slice [c0,c1); does not free `in`
     int forward(const Batch& in, int c0, int c1, Batch* out) {
         if (!prepared) return RS_ERR_STATE;
-        if (eq == E_ACTIVATION_RELU) return RS_ERR_STATE;   // DoReFa ReLU path (f4) is not part of this engine
         const int cl = c1 - c0;
         uint32_t* cur = nullptr;       // linear-part result, rows (h,w,cl)
         size_t cur_count = 0;
@@ -376,7 +442,7 @@ public:
             rs_conv_desc d{};
             d.in_h = cin_h; d.in_w = cin_w; d.in_dep = cin_dep; d.out_h = cout_h; d.out_w = cout_w; d.out_dep = cl;
             d.win_h = np.conv.window.h; d.win_w = np.conv.window.w; d.stride_h = np.conv.stride.h; d.stride_w = np.conv.stride.w;
-            d.ofs_h = ofs_h; d.ofs_w = ofs_w; d.int_mode = int_inputs ? 1 : 0; d.od_begin = 0; d.od_end = cl;
+            d.ofs_h = ofs_h; d.ofs_w = ofs_w; d.int_mode = (int_inputs && !twin_conv) ? 1 : 0; d.od_begin = 0; d.od_end = cl;
             cur_count = (size_t)cout_h * cout_w * cl;
             RS_TRY(alloc(cur_count, &cur));
             RS_TRY(rs_lwe_conv(ctx, cur, in.dev, (const int8_t*)cw->packed, (const uint32_t*)cw->bias, &d));
@@ -405,6 +471,14 @@ public:
             RS_TRY(id->apply(cur, in.dev));
         }
         if (eq == E_ACTIVATION_NONE) { out->dev = cur; out->count = cur_count; return RS_OK; }   // Quantize::add_bias
+        if (is_relu()) {   // ONE test-vector bootstrap per neuron (rows are channel-fastest: row % cl = local channel)
+            void* lut = nullptr;
+            RS_TRY(relu_tables(c0, c1, &lut));
+            RS_TRY(rs_pbs_lut_batch(ctx, cur, cur, cur_count, (const uint32_t*)lut, cl));
+            RS_TRY(rs_lwe_add_const(ctx, cur, cur_count, relu_half()));
+            out->dev = cur; out->count = cur_count;
+            return RS_OK;
+        }
 
         // ---- sign activation: ONE batched bootstrap for every neuron of the (sliced) layer
         if (!has_maxpool) {
@@ -433,6 +507,7 @@ public:
     }
 
     size_t bootstraps(int cl) {
+        if (is_relu()) return (size_t)q_h * q_w * cl;
         if (eq != E_ACTIVATION_SIGN) return 0;
         size_t n = (size_t)q_h * q_w * cl;
         if (has_maxpool) {
@@ -489,6 +564,8 @@ Batch Layer::execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int*
 size_t Layer::out_count() const { return impl_->final_h() * impl_->final_w() * (size_t)impl_->channels(); }
 int Layer::out_channels() const { return impl_->channels(); }
 size_t Layer::bootstraps() const { return impl_->bootstraps(impl_->channels()); }
+void Layer::set_int_conv_twin(bool on) { impl_->twin_conv = on; }
+bool Layer::is_relu() const { return impl_->is_relu(); }
 
 // ---------------------------------------------------------------------------------------------------- Net
 Layer* Net::add(bool int_layer, eConvType ec, uint16_t depth, ePoolType ep, eQuantType eq, tNetParams* np) {
@@ -497,6 +574,11 @@ Layer* Net::add(bool int_layer, eConvType ec, uint16_t depth, ePoolType ep, eQua
     return layers_.back().get();
 }
 int Net::prep(FILE* weights, tDimensions* dim) {
+    // a net with DoReFa-ReLU layers follows the plaintext twin's IntFunc conv convention throughout (its weights were
+    // converted for it; the reference's encrypted branch of those nets is not functional)
+    bool any_relu = false;
+    for (auto& l : layers_) any_relu = any_relu || l->is_relu();
+    if (any_relu) for (auto& l : layers_) l->set_int_conv_twin(true);
     for (auto& l : layers_) if (!l->prep(weights, dim)) return RS_ERR_ARG;
     return RS_OK;
 }
@@ -547,13 +629,17 @@ int rs_net_add_layer(rs_net* n, int int_layer, int conv_type, int out_depth, int
 }
 
 int rs_net_prep(rs_net* n, const char* weights_path, int in_h, int in_w, int in_dep) {
+    return rs_net_prep_ex(n, weights_path, in_h, in_w, in_dep, 9, 255 * 2, 255.0f);   // nets/mnist/sign1024x1/net.cpp:100-105
+}
+
+int rs_net_prep_ex(rs_net* n, const char* weights_path, int in_h, int in_w, int in_dep, int in_bits, int up_bound, float scale) {
     if (!n || !weights_path) return RS_ERR_ARG;
     FILE* fd = fopen(weights_path, "rb");
     if (!fd) return RS_ERR_ARG;
     tDimensions dim{};
     dim.hw = {(int16_t)in_h, (int16_t)in_w}; dim.in_dep = (uint32_t)in_dep;
-    dim.in_bits = 9; dim.out_bits = SINGLE_BIT; dim.filter_bits = SINGLE_BIT; dim.bias_bits = SINGLE_BIT;
-    dim.up_bound = 255 * 2; dim.scale = 255;   // nets/mnist/sign1024x1/net.cpp:100-105
+    dim.in_bits = (uint8_t)in_bits; dim.out_bits = SINGLE_BIT; dim.filter_bits = SINGLE_BIT; dim.bias_bits = SINGLE_BIT;
+    dim.up_bound = (uint32_t)up_bound; dim.scale = scale;
     int rc = n->net.prep(fd, &dim);
     // the file must be consumed exactly (format check of SURVEY.md 5.4)
     if (rc == RS_OK) { int c = fgetc(fd); if (c != EOF) rc = RS_ERR_ARG; }

@@ -269,6 +269,12 @@ lwe_lincomb_kernel(uint32_t* __restrict__ out, int out_count, const uint32_t* __
     }
 }
 
+// b word of every row += value: adds the trivial sample (0,value) (lweNoiselessTrivial + lweAddTo, lib/BinOps_enc.cpp:137-141)
+__global__ void lwe_add_const_kernel(uint32_t* __restrict__ rows, size_t count, uint32_t value) {
+    for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < count; c += (size_t)gridDim.x * blockDim.x)
+        rows[c * LWE_STRIDE + LWE_N] += value;
+}
+
 // ---------------------------------------------------------------- [world][pixels][c_local] -> [pixels][world*c_local]
 __global__ void lwe_interleave_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, size_t pixels, int c_local, int world) {
     const size_t rows = pixels * (size_t)c_local * world;

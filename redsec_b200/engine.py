@@ -109,6 +109,24 @@ class Engine:
         self._chk(self.lib.rs_pbs_batch(self.ctx, out.ptr, inp.ptr, inp.count, mu & 0xFFFFFFFF))
         return out
 
+    def pbs_lut(self, inp: LweArray, luts: np.ndarray, out: LweArray | None = None) -> LweArray:
+        """rs_pbs_lut_batch: ciphertext c is bootstrapped with test vector luts[c % len(luts)] (uint32 [m][1024])."""
+        luts = np.ascontiguousarray(luts, dtype=np.uint32).reshape(-1, TLWE_N)
+        out = out or self.alloc(inp.count)
+        dev = C.c_void_p()
+        self._chk(self.lib.rs_dev_alloc(self.ctx, luts.nbytes, C.byref(dev)))
+        try:
+            self._chk(self.lib.rs_dev_upload(self.ctx, dev.value, luts.ctypes.data, luts.nbytes))
+            self._chk(self.lib.rs_pbs_lut_batch(self.ctx, out.ptr, inp.ptr, inp.count, dev.value, luts.shape[0]))
+            self.sync()
+        finally:
+            self.lib.rs_dev_free(self.ctx, dev.value)
+        return out
+
+    def add_const(self, arr: LweArray, value: int) -> LweArray:
+        self._chk(self.lib.rs_lwe_add_const(self.ctx, arr.ptr, arr.count, value & 0xFFFFFFFF))
+        return arr
+
     def gate(self, op: str, a: LweArray, b: LweArray, mu: int, out: LweArray | None = None) -> LweArray:
         out = out or self.alloc(a.count)
         self._chk(self.lib.rs_gate_batch(self.ctx, GATE[op], out.ptr, a.ptr, b.ptr, a.count, mu & 0xFFFFFFFF))

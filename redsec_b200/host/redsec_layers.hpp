@@ -75,7 +75,11 @@ public:
     Batch execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int* ch_end);
     size_t out_count() const;                             // ciphertexts in the full output
     int out_channels() const;
-    size_t bootstraps() const;                            // PBS issued per execute (sign + OR tree)
+    size_t bootstraps() const;                            // PBS issued per execute (sign + OR tree, or one per ReLU neuron)
+    // IntFunc conv convention (call before prep): false (default) = the reference's encrypted branch, true = its plaintext
+    // twin (weight -1 contributes -x-1, zero weight 0); Net::prep switches every layer of a ReLU net to the twin.
+    void set_int_conv_twin(bool on);
+    bool is_relu() const;
     tDimensions in_dim{}, out_dim{};
 private:
     std::unique_ptr<LayerImpl> impl_;

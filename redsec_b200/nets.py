@@ -32,11 +32,15 @@ class EncryptedNet:
         for ls in spec["layers"]:
             p = LayerParams(ls["conv_win"][0], ls["conv_win"][1], ls["conv_stride"][0], ls["conv_stride"][1], int(ls["conv_same_pad"]),
                             ls["pool_win"][0], ls["pool_win"][1], ls["pool_stride"][0], ls["pool_stride"][1], int(ls["pool_same_pad"]),
-                            ls["e_bias"], 1, ls["version"])
+                            ls["e_bias"], ls.get("shift_bits") or 1, ls["version"])
             eng._chk(self.lib.rs_net_add_layer(self.net, int(ls["kind"] == "int"), CONV[ls["conv"]], ls["depth"], POOL[ls["pool"]],
                                                ACT[ls["act"]], C.byref(p)))
         h, w, c = spec["input"]
-        rc = self.lib.rs_net_prep(self.net, spec["weights"].encode(), h, w, c)
+        if "input_scale" in spec:      # the generated net's input tDimensions (nets/mnist/relu1024x1/net.cpp:96-110)
+            rc = self.lib.rs_net_prep_ex(self.net, spec["weights"].encode(), h, w, c, spec.get("input_bits", 2),
+                                         spec.get("input_up_bound", 2), float(spec["input_scale"]))
+        else:
+            rc = self.lib.rs_net_prep(self.net, spec["weights"].encode(), h, w, c)
         if rc != 0:
             raise RsError(f"rs_net_prep({spec['weights']}) failed with code {rc} (bad or mismatching weight file)")
         self.num_layers = self.lib.rs_net_num_layers(self.net)

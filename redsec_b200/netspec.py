@@ -17,10 +17,10 @@ ACT = {"none": 0, "sign": 1, "relu": 2}
 
 
 def _layer(kind, conv, depth, pool, act, conv_win=(1, 1), conv_stride=(1, 1), conv_same_pad=False,
-           pool_win=(2, 2), pool_stride=(2, 2), pool_same_pad=False, e_bias=0, version=2):
+           pool_win=(2, 2), pool_stride=(2, 2), pool_same_pad=False, e_bias=0, version=2, shift_bits=0):
     return dict(kind=kind, conv=conv, depth=depth, pool=pool, act=act, conv_win=conv_win, conv_stride=conv_stride,
                 conv_same_pad=conv_same_pad, pool_win=pool_win, pool_stride=pool_stride, pool_same_pad=pool_same_pad,
-                e_bias=e_bias, version=version)
+                e_bias=e_bias, version=version, shift_bits=shift_bits)
 
 
 def mnist_sign(n_hidden: int) -> dict:
@@ -30,6 +30,17 @@ def mnist_sign(n_hidden: int) -> dict:
     name = f"mnist/sign1024x{n_hidden}"
     return dict(name=name, input=(28, 28, 1), layers=layers, weights=os.path.join(DATA, "nets", name, "var_prep.dat"),
                 image=os.path.join(DATA, "client", "mnist_test.csv"))
+
+
+def mnist_relu(n_hidden: int) -> dict:
+    """nets/mnist/relu1024x{1,2,3}/net.cpp:96-170: all-IntLayer MLP with 4-bit DoReFa ReLU.
+    Inputs are ternarised pixels x = pixel/100 - 1 (nets/mnist/relu1024x1/main.cpp:203), lay_dim.scale = 1."""
+    layers = [_layer("int", "none", 1, "sum", "none")]
+    layers += [_layer("int", "fc", 1024, "none", "relu", e_bias=2, shift_bits=4) for _ in range(n_hidden)]
+    layers += [_layer("int", "fc", 10, "none", "none")]
+    name = f"mnist/relu1024x{n_hidden}"
+    return dict(name=name, input=(28, 28, 1), layers=layers, weights=os.path.join(DATA, "nets", name, "var_prep.dat"),
+                image=os.path.join(DATA, "client", "mnist_test.csv"), input_scale=1, input_map="relu")
 
 
 def cifar_binarynet(small: bool = False) -> dict:
@@ -65,6 +76,9 @@ NETS = {
     "mnist/sign1024x1": lambda: mnist_sign(1),
     "mnist/sign1024x2": lambda: mnist_sign(2),
     "mnist/sign1024x3": lambda: mnist_sign(3),
+    "mnist/relu1024x1": lambda: mnist_relu(1),
+    "mnist/relu1024x2": lambda: mnist_relu(2),
+    "mnist/relu1024x3": lambda: mnist_relu(3),
     "cifar/binarynet": lambda: cifar_binarynet(False),
     "cifar/binarynet_small": lambda: cifar_binarynet(True),
     "mnist/cnn_builder": mnist_cnn,
@@ -77,6 +91,18 @@ def load_image_csv(path: str, row: int = 0):
         lines = [l for l in f.read().splitlines() if l and l[0].isdigit()]
     vals = [int(v) for v in lines[row].split(",") if v != ""]
     return vals[0], vals[1:]
+
+
+def map_pixels(spec: dict, pixels):
+    """Pixel -> plaintext integer the client encrypts: 2p-255 (client/encrypt_image.cpp:76), 5-bit 2(p>>3)-31 for the
+    builder CNN, or the ternarised p/100-1 of the ReLU nets (nets/mnist/relu1024x1/main.cpp:203)."""
+    import numpy as np
+    px = np.asarray(pixels, dtype=np.int64)
+    if spec.get("input_map") == "relu":
+        return px // 100 - 1
+    if spec.get("five_bit_inputs"):
+        return 2 * (px >> 3) - 31
+    return 2 * px - 255
 
 
 # ---------------------------------------------------------------------------------------------- synthetic weights

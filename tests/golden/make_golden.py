@@ -11,10 +11,15 @@ subprocess.check_call([os.path.join(ROOT, "oracle", "build_ref.sh")])
 out = {}
 cases = [("mnist/sign1024x1", "client/mnist_test.csv", 1), ("mnist/sign1024x2", "client/mnist_test.csv", 1),
          ("mnist/sign1024x3", "client/mnist_test.csv", 1), ("cifar/binarynet", "client/cifar_test.csv", 1),
-         ("cifar/binarynet_small", "client/cifar_test.csv", 1), ("mnist/sign1024x1", "nets/mnist/mnist_data.csv", 20)]
+         ("cifar/binarynet_small", "client/cifar_test.csv", 1), ("mnist/sign1024x1", "nets/mnist/mnist_data.csv", 20),
+         # DoReFa-ReLU nets (row f4): inputs x = pixel/100 - 1 (nets/mnist/relu1024x1/main.cpp:203)
+         ("mnist/relu1024x1", "client/mnist_test.csv", 1), ("mnist/relu1024x2", "client/mnist_test.csv", 1),
+         ("mnist/relu1024x3", "client/mnist_test.csv", 1), ("mnist/relu1024x1", "nets/mnist/mnist_data.csv", 20),
+         ("mnist/relu1024x2", "nets/mnist/mnist_data.csv", 20), ("mnist/relu1024x3", "nets/mnist/mnist_data.csv", 20)]
 for net, csv, rows in cases:
     exe = os.path.join(ROOT, "oracle", "_ref", "ptxt_" + net.replace("/", "_"))
-    txt = subprocess.check_output([exe, os.path.join(REF, csv), str(rows)], cwd=os.path.join(REF, "nets", net), text=True)
+    extra = ["relu"] if "relu" in net else []
+    txt = subprocess.check_output([exe, os.path.join(REF, csv), str(rows)] + extra, cwd=os.path.join(REF, "nets", net), text=True)
     res = []
     for line in txt.splitlines():
         if line.startswith("label"):

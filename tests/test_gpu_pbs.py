@@ -64,6 +64,37 @@ def test_pbs_bit_exact_and_decrypts(oracle, keyset, engine, count):
     assert np.array_equal(dec, np.where(bits == 1, 1, -1))
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_test_vector_bootstrap_bit_exact(oracle, keyset, engine, variant):
+    """rs_pbs_lut_batch (row f4): per-ciphertext test vectors, ciphertext c uses table c % m.  Bit-exact vs the oracle and the
+    output decrypts to the table entry of the slot the rotation ends on, on both halves of the torus."""
+    from oracle import layers_oracle as LO
+    rng = np.random.default_rng(31)
+    luts = (rng.integers(-2000, 2000, size=(5, 1024)) * LO.UNIT & 0xFFFFFFFF).astype(np.uint32)
+    msgs = (rng.integers(-2048, 2048, size=37) * LO.UNIT & 0xFFFFFFFF).astype(np.uint32)
+    ct = oracle.encrypt(msgs, 2.0 ** -15, keyset.lwe_key, 6)
+    engine.set_tuning(variant)
+    try:
+        got = engine.download(engine.pbs_lut(engine.upload(ct), luts))
+    finally:
+        engine.set_tuning(0)
+    assert np.array_equal(got, oracle.pbs_lut(ct, luts, keyset))
+    want, slot = LO.predicted_lut_message(ct, luts, keyset.lwe_key)
+    err = (oracle.phase(got, keyset.lwe_key).astype(np.int64) - want.astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.max(np.abs(err)) < LO.UNIT // 4 and len(set(slot // 1024)) == 2
+
+
+def test_test_vector_bootstrap_rejected_by_tensor_memory_variant(engine, oracle, keyset):
+    import redsec_b200 as rs
+    ct = oracle.encrypt(np.zeros(4, np.uint32), 2.0 ** -15, keyset.lwe_key, 1)
+    engine.set_tuning(3)
+    try:
+        with pytest.raises(rs.RsError):
+            engine.pbs_lut(engine.upload(ct), np.zeros((1, 1024), np.uint32))
+    finally:
+        engine.set_tuning(0)
+
+
 @pytest.mark.parametrize("groups", [0, 1, 2, 3, 4])
 def test_variants_agree(oracle, keyset, engine, groups):
     bits, ct = _rand_bits_ct(oracle, keyset, 29, MU8, 2.0 ** -25, 77)

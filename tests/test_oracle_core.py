@@ -77,3 +77,24 @@ def test_sign_bootstrap_maps_zero_phase_to_plus_mu(oracle, keyset):
     ct = np.zeros((1, 351), np.uint32)
     out = O.pbs(ct, 1 << 20, keyset)
     assert O.decrypt(out, keyset.lwe_key, 4096)[0] == 1
+
+
+def test_test_vector_bootstrap_exact_fft_and_slot_semantics(oracle, keyset):
+    """Row f4: programmable bootstrap with caller-supplied test vectors.  Exact-integer and FFT variants agree bit for bit;
+    the output decrypts to the table entry of the slot the blind rotation ends on (negated on the upper half of the torus);
+    a constant table reproduces the sign bootstrap."""
+    from oracle import layers_oracle as LO
+    O = oracle
+    rng = np.random.default_rng(21)
+    luts = (rng.integers(-2000, 2000, size=(3, 1024)) * LO.UNIT & 0xFFFFFFFF).astype(np.uint32)
+    msgs = (rng.integers(-2048, 2048, size=6) * LO.UNIT & 0xFFFFFFFF).astype(np.uint32)
+    ct = O.encrypt(msgs, 2.0 ** -15, keyset.lwe_key, 5)
+    fft = O.pbs_lut(ct, luts, keyset)
+    assert np.array_equal(fft[:2], O.pbs_lut(ct[:2], luts, keyset, exact=True))
+    want, slot = LO.predicted_lut_message(ct, luts, keyset.lwe_key)
+    got = O.phase(fft, keyset.lwe_key)
+    err = (got.astype(np.int64) - want.astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.max(np.abs(err)) < LO.UNIT // 4           # output noise only
+    assert len(set(slot // 1024)) == 2                   # both halves of the torus were exercised
+    const = np.full((1, 1024), LO.UNIT, dtype=np.uint32)
+    assert np.array_equal(O.pbs_lut(ct[:3], const, keyset), O.pbs(ct[:3], LO.UNIT, keyset))

@@ -15,7 +15,7 @@ def _plain_scores(spec, row=0, image=None):
     from oracle import layers_oracle as LO
     layers = LO.prepare(spec, spec["weights"])
     label, px = netspec.load_image_csv(image or spec["image"], row)
-    return label, LO.plain_forward(layers, 2 * np.asarray(px) - 255)
+    return label, LO.plain_forward(layers, netspec.map_pixels(spec, px))
 
 
 @pytest.mark.parametrize("net,csv", [("mnist/sign1024x1", "client/mnist_test.csv"), ("mnist/sign1024x2", "client/mnist_test.csv"),
@@ -37,6 +37,20 @@ def test_mnist_20_rows_match_reference():
         assert label == g["label"] and list(scores) == g["scores"], row
 
 
+@pytest.mark.parametrize("net", ["mnist/relu1024x1", "mnist/relu1024x2", "mnist/relu1024x3"])
+def test_relu_nets_plain_scores_match_reference(net):
+    """Row f4: the DoReFa-ReLU restatement (slope multiply, bias, arithmetic shift, clamp; ~x for weight -1) reproduces the
+    reference's plaintext build on the client image and on 20 MNIST rows."""
+    spec = netspec.NETS[net]()
+    label, scores = _plain_scores(spec)
+    gold = GOLD[f"{net}|client/mnist_test.csv|1"][0]
+    assert label == gold["label"] and list(scores) == gold["scores"]
+    img = os.path.join(netspec.DATA, "nets", "mnist", "mnist_data_20.csv")
+    for row, g in enumerate(GOLD[f"{net}|nets/mnist/mnist_data.csv|20"]):
+        label, scores = _plain_scores(spec, row, img)
+        assert label == g["label"] and list(scores) == g["scores"], row
+
+
 def test_cifar_small_plain_scores_match_reference():
     spec = netspec.NETS["cifar/binarynet_small"]()
     label, scores = _plain_scores(spec)
@@ -47,3 +61,29 @@ def test_cifar_small_plain_scores_match_reference():
 def test_weight_file_size_identity():
     # sign1024x1 = 5 + (1+50176) + (1+4096) + (1+2560) + (1+40) bytes
     assert os.path.getsize(netspec.NETS["mnist/sign1024x1"]()["weights"]) == 56881
+
+
+def test_relu_test_vectors_reproduce_the_staircase():
+    """The encrypted ReLU's per-channel tables: reading slot x/2 (with the negacyclic sign on the upper half) and adding the
+    constant back gives the plaintext staircase at every even x in [-2048, 2048)."""
+    from oracle import layers_oracle as LO
+    spec = netspec.NETS["mnist/relu1024x2"]()
+    layers = LO.prepare(spec, spec["weights"])
+    for L in layers[1:3]:
+        assert (L.shift_bits, L.slope_bits) == ((4, 6) if L is layers[1] else (4, 8))
+        tv, half = LO.relu_test_vectors(L)
+        xs = np.arange(-2048, 2048, 2)
+        slot = (xs // 2) % 2048
+        v = tv[:, slot % 1024].astype(np.int64)
+        got = ((np.where(slot < 1024, v, -v) + half) & 0xFFFFFFFF) // LO.UNIT
+        want = LO.relu_shift(L, np.broadcast_to(xs[:, None], (xs.size, tv.shape[0]))).T
+        inner = np.abs(xs) < 1024                        # small |x|: exact by construction
+        assert np.array_equal(got[:, inner], want[:, inner])
+        # beyond +-1024 the table is the negacyclic image g(x +- 2048) = -g(x) of the inner part: exact wherever x and
+        # x -+ 2048 are saturated at opposite ends, i.e. up to |x| < 2048 - |transition position|
+        mid = np.abs(xs) < 512
+        lo, hi = want[:, mid][:, 0], want[:, mid][:, -1]
+        sat = ((lo == 0) & (hi == 15)) | ((lo == 15) & (hi == 0))      # transition inside (-512, 512)
+        assert sat.sum() > 100
+        wide = np.abs(xs) < 1536
+        assert np.array_equal(got[sat][:, wide], want[sat][:, wide])
