@@ -340,6 +340,7 @@ def nets_seconds_per_image(eng, ks, client, dist, rank: int, world: int, names) 
             label, px = netspec.load_image_csv(spec["image"])
             ct = client.encrypt_image(px, ks.lwe_key, seed=7)
             net = nets.EncryptedNet(eng, spec)
+            net.build_tables(rank, world)                     # weights/tables on the device before the timed window (as prep() does)
             d = eng.upload(ct)
             distinfo = (dist, rank, world) if dist is not None else None
             if name.startswith("mnist"):

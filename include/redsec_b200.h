@@ -170,6 +170,10 @@ int rs_net_prep(rs_net *net, const char *weights_path /* var_prep.dat */, int in
 /* same with the input tDimensions of the generated net spelled out (lay_dim.in_bits / up_bound / scale,
  * nets/mnist/relu1024x1/net.cpp:96-110: 2, 2, 1); rs_net_prep uses the sign nets' 9, 510, 255 */
 int rs_net_prep_ex(rs_net *net, const char *weights_path, int in_h, int in_w, int in_dep, int in_bits, int up_bound, float scale);
+/* optional, after rs_net_prep: build and upload the device tables (packed weights, pooling rows, OR trees, ReLU test vectors) of
+ * rank's channel slices now rather than lazily inside the first forward -- the counterpart of the weight loading that
+ * {Bin,Int}Layer::prep does before the reference's "Inference Time" window (nets/mnist/sign1024x1/main.cu:72-78) */
+int rs_net_build_tables(rs_net *net, int rank, int world);
 int rs_net_num_layers(const rs_net *net);
 int rs_net_layer_info(rs_net *net, int layer, size_t *out_count, int *channels, size_t *bootstraps, int *out_h, int *out_w);
 /* forward of one layer for rank's output-channel slice (world=1: whole layer).  Does not free in_dev; the caller

@@ -62,6 +62,7 @@ SIGNATURES = {
     "rs_net_add_layer": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "rs_net_prep": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "rs_net_prep_ex": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
+    "rs_net_build_tables": (C.c_int, [vp, C.c_int, C.c_int]),
     "rs_net_num_layers": (C.c_int, [vp]),
     "rs_net_layer_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rs_net_layer_forward": (C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

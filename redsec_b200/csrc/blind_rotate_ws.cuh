@@ -15,7 +15,8 @@
 //   * warpgroups 0,1 = 8 BACK warps, two per ciphertext.  A back warp reads a row from the exchange ring, runs passes 2
 //     and 3 (twiddles fused as FMAs, exchange 2 through shuffles), multiplies by the BSK slab and accumulates in
 //     registers (Fourier accumulators, 64 registers).  After 20 rows the pair runs both inverse transforms (their
-//     exchange 1 goes through the idle ring slots 0 and 1), rounds, adds into the accumulator and signals acc_ready.
+//     exchange 1 goes through the ring slot of the step's last row, released afterwards), rounds, adds into the
+//     accumulator and signals acc_ready per polynomial, polynomial 0 first, so the front warp restarts early.
 //   The two back warps of a ciphertext never synchronise with each other during the 20 rows (exchange 1 is now
 //   front -> back, exchange 2 is intra-warp); all hand-offs are mbarriers, so the roles drift freely within the rings.
 //   * Registers are redistributed with setmaxnreg: launch at 168/thread (12 warps), front warps drop to 120, back warps
@@ -68,13 +69,13 @@ struct WsSmem {
     static constexpr int kStagesOff = 0;
     static constexpr int kCtOff = STAGES * kStageBytes;
     static constexpr int kBarOff = kCtOff + kCts * kCtBytes;
-    // barriers (8 B each): bsk_full[STAGES], bsk_empty[STAGES], x_full[4][XSLOTS], x_empty[4][XSLOTS], acc_ready[4]
+    // barriers (8 B each): bsk_full[STAGES], bsk_empty[STAGES], x_full[4][XSLOTS], x_empty[4][XSLOTS], acc_ready[4][2]
     static constexpr int kBskFull = 0, kBskEmpty = STAGES, kXFull = 2 * STAGES, kXEmpty = kXFull + kCts * XSLOTS,
-                         kAccReady = kXEmpty + kCts * XSLOTS, kNumBars = kAccReady + kCts;
+                         kAccReady = kXEmpty + kCts * XSLOTS, kNumBars = kAccReady + 2 * kCts;   // acc_ready[4][2]: one per accumulator polynomial
     static constexpr int kIssuedOff = kBarOff + kNumBars * 8;
     static constexpr int kTotal = kIssuedOff + 8;
     static_assert(kCtBytes % 16 == 0, "ciphertext block must stay 16-byte aligned");
-    static_assert(XSLOTS >= 2, "inverse hand-off uses slots 0 and 1");
+    static_assert(XSLOTS >= 3, "the inverse holds one slot; the front warp needs two more to run ahead");
 };
 
 template <int N_REGS>
@@ -118,7 +119,8 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 mbar_init(bar_base + (S::kXFull + j * XSLOTS + x) * 8, 1);   // the front warp
                 mbar_init(bar_base + (S::kXEmpty + j * XSLOTS + x) * 8, 2);  // the two back warps
             }
-            mbar_init(bar_base + (S::kAccReady + j) * 8, 2);               // the two back warps
+            mbar_init(bar_base + (S::kAccReady + 2 * j) * 8, 2);           // the two back warps, accumulator polynomial 0
+            mbar_init(bar_base + (S::kAccReady + 2 * j + 1) * 8, 2);       // ... polynomial 1
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *issued = 0;
@@ -136,7 +138,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         uint16_t* bara = reinterpret_cast<uint16_t*>(cbase + S::kAccBytes);
         double2* ring = reinterpret_cast<double2*>(cbase + S::kAccBytes + S::kBaraBytes);
         const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
-        const uint32_t accready = bar_base + (S::kAccReady + j) * 8;
+        const uint32_t accready = bar_base + (S::kAccReady + 2 * j) * 8;   // [2]: per accumulator polynomial
         const uint8_t* bsk_bytes = reinterpret_cast<const uint8_t*>(bsk_f);
         const uint64_t l2pol = l2_policy_evict_last(l2_keep);
 
@@ -157,12 +159,14 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         WSP_DECL;
 #pragma unroll 1
         for (int i = 0; i < LWE_N; i++) {
-            WSP(7);
-            if (i > 0) mbar_wait_warp_long(accready, (i - 1) & 1);   // back warps have added step i-1 into the accumulator
-            WSP(0);
             const int a = bara[i];
 #pragma unroll 1
             for (int c = 0; c < 2; c++) {
+                WSP(7);
+                // the back warps have added step i-1 into accumulator polynomial c.  Polynomial 0 is released first, so the rows of
+                // c = 0 are produced while the back warps still run the inverse transform of polynomial 1 (no bubble at the step boundary)
+                if (i > 0) mbar_wait_warp_long(accready + c * 8, (i - 1) & 1);
+                WSP(0);
                 uint32_t src[2][16];   // (X^a - 1)*acc_c + decomposition offset at this lane's 2 x 16 coefficients
 #pragma unroll
                 for (int hf = 0; hf < 2; hf++) {
@@ -226,7 +230,8 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             }
         }
         WSP_FLUSH();
-        mbar_wait_warp_long(accready, (LWE_N - 1) & 1);     // the last step's accumulator update
+        mbar_wait_warp_long(accready, (LWE_N - 1) & 1);     // the last step's accumulator update, both polynomials
+        mbar_wait_warp_long(accready + 8, (LWE_N - 1) & 1);
         // ---- sample extract: a'[0]=acc_a[0], a'[k]=-acc_a[N-k], b'=acc_b[0]
         uint32_t* ext = ext_out + (size_t)ct * EXT_STRIDE;
         for (int k = lane; k < N; k += 32) ext[k] = (k == 0) ? acc[0] : 0u - acc[N - k];
@@ -243,7 +248,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     uint8_t* cbase = smem + S::kCtOff + j * S::kCtBytes;
     double2* ring = reinterpret_cast<double2*>(cbase + S::kAccBytes + S::kBaraBytes);
     const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
-    const uint32_t accready = bar_base + (S::kAccReady + j) * 8;
+    const uint32_t accready = bar_base + (S::kAccReady + 2 * j) * 8;   // [2]: per accumulator polynomial
     uint32_t* acc = reinterpret_cast<uint32_t*>(cbase);
     Twiddles tw;
     make_twiddles(tw, u);
@@ -272,7 +277,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             for (int q2 = 0; q2 < 8; q2++) v[q2] = buf[rr * 64 + lo + 8 * q2];
             dft8_twiddled<-1, false>(v, [&](int q) { return tw.g[q]; });
             __syncwarp();
-            if (lane == 0) mbar_arrive(xempty + slot * 8);      // the row has been consumed into registers
+            // the row has been consumed into registers.  The LAST row of a step keeps its slot: the inverse transforms below use it
+            // as their exchange buffer and release it afterwards, so the front warp can refill the other slots meanwhile
+            if (lane == 0 && row != 2 * BK_L - 1) mbar_arrive(xempty + slot * 8);
             rotate_exchange(v, lo);
             // the first BSK operands are requested before pass 3 when the slab is already resident (the common case), so that
             // their shared-memory latency overlaps the butterflies instead of stalling the first FMA of the MAC
@@ -304,29 +311,24 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             WSP(3);
         }
         // ---- inverse transforms, round to nearest, accumulate into acc (exact integers mod 2^32).  Exchange 1 of the
-        // inverse crosses the two back warps: it goes through ring slots 0 and 1, which are idle here (the front warp
-        // cannot produce the next step's rows before it has seen acc_ready).
-        group_sync(j);      // both back warps are done reading the step's forward rows
-        auto inverse_head = [&](double2 (&f)[8], int poly) {
+        // inverse crosses the two back warps: it goes through the ring slot of the step's last forward row, which this pair
+        // has not released yet.  Polynomial 0 is finished and published first (acc_ready[0]) so that the front warp produces
+        // the next step's first rows into the two free slots while polynomial 1 is still being transformed.
+        double2* ibuf = ring + ((rowc - 1) % XSLOTS) * FFT_BUF;
+        auto inverse_poly = [&](double2 (&f)[8], int poly) {
+            group_sync(j);      // both back warps are done reading ibuf (the last forward row / the previous polynomial)
             dft8<+1>(f);
             f[0] = cmul_conj(f[0], tw.h[0]);
 #pragma unroll
             for (int k = 1; k < 8; k++) f[k] = cmul_conj(f[k], tw.h[8 - k]);
             rotate_exchange(f, lo);
             dft8<-1>(f);
-            double2* buf = ring + poly * FFT_BUF;
 #pragma unroll
-            for (int q2 = 0; q2 < 8; q2++) buf[rr * 64 + lo + 8 * q2] = cmul_conj(f[q2], tw.g[q2]);
-        };
-        inverse_head(f0, 0);
-        inverse_head(f1, 1);
-        group_sync(j);
-#pragma unroll 1
-        for (int poly = 0; poly < 2; poly++) {
-            const double2* buf = ring + poly * FFT_BUF;
+            for (int q2 = 0; q2 < 8; q2++) ibuf[rr * 64 + lo + 8 * q2] = cmul_conj(f[q2], tw.g[q2]);
+            group_sync(j);
             double2 v[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) v[r] = buf[r * 64 + u];
+            for (int r = 0; r < 8; r++) v[r] = ibuf[r * 64 + u];
             dft8<+1>(v);
             v[0] = make_double2(v[0].x * (1.0 / 512.0), v[0].y * (1.0 / 512.0));
 #pragma unroll
@@ -341,9 +343,12 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 acc[poly * N + u + 64 * q] += (uint32_t)__double2ll_rn(v[q].x);
                 acc[poly * N + u + 64 * q + NH] += (uint32_t)__double2ll_rn(v[q].y);
             }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(accready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accready + poly * 8);
+        };
+        inverse_poly(f0, 0);
+        inverse_poly(f1, 1);
+        if (lane == 0) mbar_arrive(xempty + ((rowc - 1) % XSLOTS) * 8);    // the last row's slot, held for the inverse exchange
         WSP(4);
     }
     WSP_FLUSH();

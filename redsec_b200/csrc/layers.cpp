@@ -125,7 +125,8 @@ public:
     int mp_out_h = 0, mp_out_w = 0;
     // caches keyed by channel slice
     std::map<std::pair<int, int>, ConvWeights> conv_cache;
-    std::map<std::pair<int, int>, std::unique_ptr<DevCsr>> sumpool_cache, identity_cache;
+    typedef std::pair<std::pair<int, int>, std::pair<int, int>> SliceKey;   // (channel range, output-pixel range)
+    std::map<SliceKey, std::unique_ptr<DevCsr>> sumpool_cache, identity_cache;
     std::map<int, std::unique_ptr<PoolPlan>> maxpool_cache;
     std::map<std::pair<int, int>, void*> relu_cache;
 
@@ -277,8 +278,9 @@ public:
     }
 
     // sum-pool over a local channel slice; rows (oph,opw,cl), inputs (ih,iw,cl) (lib/IntFunc.cpp:665-697)
-    int sumpool_table(int c0, int c1, DevCsr** out) {
-        auto key = std::make_pair(c0, c1);
+    int sumpool_table(int c0, int c1, DevCsr** out, int p0 = 0, int p1 = -1) {
+        if (p1 < 0) p1 = sp_out_h * sp_out_w;
+        auto key = std::make_pair(std::make_pair(c0, c1), std::make_pair(p0, p1));
         auto it = sumpool_cache.find(key);
         if (it == sumpool_cache.end()) {
             const tPoolParams& pl = np.pool;
@@ -287,6 +289,7 @@ public:
             for (int oph = 0; oph < sp_out_h; oph++)
                 for (int opw = 0; opw < sp_out_w; opw++)
                     for (int c = 0; c < cl; c++) {
+                        if (oph * sp_out_w + opw < p0 || oph * sp_out_w + opw >= p1) continue;   // pixel-sharded input layers
                         const int ih0 = oph * pl.stride.h - sp_ofs_h, iw0 = opw * pl.stride.w - sp_ofs_w;
                         for (int fh = 0; fh < pl.window.h && ih0 + fh < sp_in_h; fh++) {
                             if (ih0 + fh < 0) continue;
@@ -306,12 +309,13 @@ public:
     }
 
     // bias add only (E_NO_CONV without pooling, e.g. CIFAR layer 0); input (h,w,C), output slice (h,w,cl)
-    int identity_table(int c0, int c1, DevCsr** out) {
-        auto key = std::make_pair(c0, c1);
+    int identity_table(int c0, int c1, DevCsr** out, int p0 = 0, int p1 = -1) {
+        if (p1 < 0) p1 = q_h * q_w;
+        auto key = std::make_pair(std::make_pair(c0, c1), std::make_pair(p0, p1));
         auto it = identity_cache.find(key);
         if (it == identity_cache.end()) {
             Csr csr;
-            for (int p = 0; p < q_h * q_w; p++)
+            for (int p = p0; p < p1; p++)
                 for (int c = c0; c < c1; c++) { csr.entry(p * q_dep + c, 1); csr.end_row(is_relu() ? 0u : bias_torus[c]); }
             auto dev = std::make_unique<DevCsr>();
             RS_TRY(dev->upload(ctx, csr));
@@ -427,9 +431,33 @@ public:
         return RS_OK;
     }
 
-    // ---- forward for the channel slice [c0,c1); does not free `in`
-    int forward(const Batch& in, int c0, int c1, Batch* out) {
+    // builds (and caches) every device table forward() needs for the channel slice [c0,c1): packed conv weights, pooling /
+    // bias CSR rows, the max-pool OR tree, the ReLU test vectors.  forward() builds them lazily; calling this from prep keeps
+    // the host-side packing out of the first inference, like the reference's prep() (weights are read before "Inference Time").
+    int build_tables(int c0, int c1, int p0 = 0, int p1 = -1) {
         if (!prepared) return RS_ERR_STATE;
+        if (has_conv) { ConvWeights* cw = nullptr; RS_TRY(conv_tables(c0, c1, &cw)); }
+        if (has_sumpool) {
+            if (!has_conv && (c0 != 0 || c1 != q_dep)) return RS_ERR_ARG;
+            DevCsr* sp = nullptr; RS_TRY(sumpool_table(c0, c1, &sp, has_conv ? 0 : p0, has_conv ? -1 : p1));
+        }
+        if (!has_conv && !has_sumpool) { DevCsr* id = nullptr; RS_TRY(identity_table(c0, c1, &id, p0, p1)); }
+        if (is_relu()) { void* lut = nullptr; RS_TRY(relu_tables(c0, c1, &lut)); }
+        if (has_maxpool && eq == E_ACTIVATION_SIGN) { PoolPlan* plan = nullptr; RS_TRY(maxpool_plan(c1 - c0, &plan)); }
+        return RS_OK;
+    }
+
+    // Layers without a conv stage (the input layers: bias / sum-pool + activation on the client's ciphertexts) have too few
+    // channels to shard by channel; they shard by OUTPUT PIXEL instead: rank r computes pixels [r*P/world, (r+1)*P/world) for all
+    // channels, and the all-gather of those row blocks is already in canonical (h,w,c) order.
+    bool pixel_shardable(int world) const {
+        return world > 1 && !has_conv && !has_maxpool && eq != E_ACTIVATION_NONE && (q_h * q_w) % world == 0;
+    }
+
+    // ---- forward for the channel slice [c0,c1) (and, for conv-less layers, the output-pixel range [p0,p1)); does not free `in`
+    int forward(const Batch& in, int c0, int c1, Batch* out, int p0 = 0, int p1 = -1) {
+        if (!prepared) return RS_ERR_STATE;
+        if (has_conv && (p0 != 0 || p1 >= 0)) return RS_ERR_ARG;
         const int cl = c1 - c0;
         uint32_t* cur = nullptr;       // linear-part result, rows (h,w,cl)
         size_t cur_count = 0;
@@ -456,7 +484,7 @@ public:
                 if (in.count != (size_t)sp_in_h * sp_in_w * q_dep) return RS_ERR_ARG;
                 src = in.dev;
             }
-            RS_TRY(sumpool_table(c0, c1, &sp));
+            RS_TRY(sumpool_table(c0, c1, &sp, has_conv ? 0 : p0, has_conv ? -1 : p1));
             RS_TRY(alloc(sp->rows, &pooled));
             RS_TRY(sp->apply(pooled, src));
             if (cur) rs_lwe_free(ctx, cur);
@@ -465,7 +493,7 @@ public:
         if (!has_conv && !has_sumpool) {
             if (in.count != (size_t)q_h * q_w * q_dep) return RS_ERR_ARG;
             DevCsr* id = nullptr;
-            RS_TRY(identity_table(c0, c1, &id));
+            RS_TRY(identity_table(c0, c1, &id, p0, p1));
             cur_count = id->rows;
             RS_TRY(alloc(cur_count, &cur));
             RS_TRY(id->apply(cur, in.dev));
@@ -555,7 +583,12 @@ Batch Layer::execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int*
     int c0 = 0, c1 = impl_->channels();
     rs_shard_range(impl_->channels(), impl_->has_conv ? 1 : 0, shard.rank, shard.world, &c0, &c1);
     Batch out;
-    if (impl_->forward(in, c0, c1, &out) != RS_OK) { out.dev = nullptr; out.count = 0; }
+    int p0 = 0, p1 = -1;
+    if (impl_->pixel_shardable(shard.world)) {
+        const int per = impl_->q_h * impl_->q_w / shard.world;
+        p0 = shard.rank * per; p1 = p0 + per;
+    }
+    if (impl_->forward(in, c0, c1, &out, p0, p1) != RS_OK) { out.dev = nullptr; out.count = 0; }
     if (ch_begin) *ch_begin = c0;
     if (ch_end) *ch_end = c1;
     return out;
@@ -564,6 +597,16 @@ Batch Layer::execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int*
 size_t Layer::out_count() const { return impl_->final_h() * impl_->final_w() * (size_t)impl_->channels(); }
 int Layer::out_channels() const { return impl_->channels(); }
 size_t Layer::bootstraps() const { return impl_->bootstraps(impl_->channels()); }
+int Layer::build_tables(ShardSpec shard) {
+    int c0 = 0, c1 = impl_->channels();
+    rs_shard_range(impl_->channels(), impl_->has_conv ? 1 : 0, shard.rank, shard.world, &c0, &c1);
+    int p0 = 0, p1 = -1;
+    if (impl_->pixel_shardable(shard.world)) {
+        const int per = impl_->q_h * impl_->q_w / shard.world;
+        p0 = shard.rank * per; p1 = p0 + per;
+    }
+    return impl_->build_tables(c0, c1, p0, p1);
+}
 void Layer::set_int_conv_twin(bool on) { impl_->twin_conv = on; }
 bool Layer::is_relu() const { return impl_->is_relu(); }
 
@@ -645,6 +688,14 @@ int rs_net_prep_ex(rs_net* n, const char* weights_path, int in_h, int in_w, int 
     if (rc == RS_OK) { int c = fgetc(fd); if (c != EOF) rc = RS_ERR_ARG; }
     fclose(fd);
     return rc;
+}
+
+int rs_net_build_tables(rs_net* n, int rank, int world) {
+    if (!n || world <= 0 || rank < 0 || rank >= world) return RS_ERR_ARG;
+    redsec::ShardSpec sh; sh.rank = rank; sh.world = world;
+    for (size_t i = 0; i < n->net.num_layers(); i++)
+        if (int rc = n->net.layer(i)->build_tables(sh)) return rc;
+    return RS_OK;
 }
 
 int rs_net_num_layers(const rs_net* n) { return n ? (int)const_cast<rs_net*>(n)->net.num_layers() : 0; }

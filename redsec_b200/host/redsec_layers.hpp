@@ -71,8 +71,12 @@ public:
     Batch execute(Batch in);                              // lib/BinLayer.cpp:122-127 (run(E_EXEC))
     // Sharded execution: computes this rank's output-channel slice [begin,end) of the layer for all pixels,
     // bootstraps and max-pools it locally; the caller all-gathers the slices (rows [pixel][c_local]) and
-    // calls interleave_shards() to restore the canonical (h,w,c) order.
+    // calls interleave_shards() to restore the canonical (h,w,c) order.  A layer without a conv stage (input layers)
+    // is sharded by output pixel instead when its pixel count divides the world size: [begin,end) is then the full
+    // channel range, the result holds out_count()/world rows, and the all-gather of those blocks is already canonical.
     Batch execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int* ch_end);
+    // uploads every device table execute()/execute_shard() needs for this rank's slice now instead of on first use
+    int build_tables(ShardSpec shard = ShardSpec());
     size_t out_count() const;                             // ciphertexts in the full output
     int out_channels() const;
     size_t bootstraps() const;                            // PBS issued per execute (sign + OR tree, or one per ReLU neuron)

@@ -45,6 +45,10 @@ class EncryptedNet:
             raise RsError(f"rs_net_prep({spec['weights']}) failed with code {rc} (bad or mismatching weight file)")
         self.num_layers = self.lib.rs_net_num_layers(self.net)
 
+    def build_tables(self, rank: int = 0, world: int = 1):
+        """Upload every device table of this rank's slices now (otherwise built lazily by the first forward)."""
+        self.eng._chk(self.lib.rs_net_build_tables(self.net, rank, world))
+
     def close(self):
         if self.net:
             self.lib.rs_net_destroy(self.net)
@@ -67,16 +71,22 @@ class EncryptedNet:
         arr._owned = True     # allocated with rs_lwe_alloc inside the library; freed through rs_lwe_free
         return arr, c0.value, c1.value
 
-    def run(self, inp: LweArray, collect: list | None = None, dist=None) -> LweArray:
-        """HeBNN::run.  dist = (torch.distributed module, rank, world) enables neuron sharding + all-gather."""
+    def run(self, inp: LweArray, collect: list | None = None, dist=None, times: list | None = None) -> LweArray:
+        """HeBNN::run.  dist = (torch.distributed module, rank, world) enables neuron sharding + all-gather.
+        times: if a list, receives the host wall-clock seconds of every layer (syncs after each layer; diagnostics only)."""
+        import time
         x = inp
         for i in range(self.num_layers):
+            t0 = time.perf_counter() if times is not None else 0.0
             if dist is None or dist[2] == 1:
                 y, _, _ = self.layer_forward(i, x)
             else:
                 y = self._layer_sharded(i, x, dist)
             if collect is not None:
                 collect.append(self.eng.download(y))
+            if times is not None:
+                self.eng.sync()
+                times.append(time.perf_counter() - t0)
             if x is not inp:
                 x.free()
             x = y
@@ -87,7 +97,8 @@ class EncryptedNet:
         td, rank, world = dist
         info = self.layer_info(i)
         y, c0, c1 = self.layer_forward(i, x, rank, world)
-        if c1 - c0 == info["channels"]:
+        pixel_sharded = c1 - c0 == info["channels"] and y.count * world == info["out_count"]
+        if c1 - c0 == info["channels"] and not pixel_sharded:
             return y                                   # layer not shardable: computed replicated on every rank
         self.eng.sync()
         dev = torch.device("cuda", self.eng.device)
@@ -97,8 +108,11 @@ class EncryptedNet:
         td.all_gather_into_tensor(gathered, local)     # NCCL over NVLink: the exchange step between layers
         torch.cuda.current_stream(dev).synchronize()
         out = self.eng.alloc(world * y.count)
-        pixels = y.count // (c1 - c0)
-        self.eng._chk(self.lib.rs_lwe_interleave(self.eng.ctx, out.ptr, gathered.data_ptr(), pixels, c1 - c0, world))
+        if pixel_sharded:                              # conv-less input layer: rank blocks of pixel rows are already canonical
+            pixels, c_local, parts = world * y.count // info["channels"], info["channels"], 1
+        else:
+            pixels, c_local, parts = y.count // (c1 - c0), c1 - c0, world
+        self.eng._chk(self.lib.rs_lwe_interleave(self.eng.ctx, out.ptr, gathered.data_ptr(), pixels, c_local, parts))
         self.eng.sync()
         y.free()
         return out

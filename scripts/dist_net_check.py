@@ -17,6 +17,7 @@ eng = rs.Engine(local); eng.load_eval_key(ks.bsk, ks.ksk)
 label, px = netspec.load_image_csv(spec["image"])
 ct = client.encrypt_image(px, ks.lwe_key, seed=7)
 net = nets.EncryptedNet(eng, spec)
+net.build_tables(rank, world)
 d = eng.upload(ct)
 out = net.run(d, dist=(dist, rank, world)); eng.sync()
 dist.barrier(); torch.cuda.synchronize()
@@ -30,6 +31,11 @@ same = None
 if name.startswith("mnist") or os.environ.get("RS_CHECK_SINGLE"):
     single = eng.download(net.run(d))
     same = bool(np.array_equal(single, sharded))
+if os.environ.get("RS_LAYER_TIMES"):
+    times = []
+    net.run(d, dist=(dist, rank, world), times=times).free()
+    if rank == 0:
+        print("layer seconds (rank 0):", [round(t, 4) for t in times], "sum", round(sum(times), 4))
 if rank == 0:
     print({"net": name, "world": world, "s_per_image": dt, "bootstraps": net.bootstraps(), "argmax": int(np.argmax(scores)),
            "label": label, "scores": scores.tolist(), "sharded_equals_single_gpu": same})

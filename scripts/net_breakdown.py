@@ -10,6 +10,7 @@ spec = netspec.NETS[name]()
 label, px = netspec.load_image_csv(spec["image"])
 ct = client.encrypt_image(px, ks.lwe_key, seed=7)
 net = nets.EncryptedNet(eng, spec)
+net.build_tables()
 d = eng.upload(ct)
 if name.startswith("mnist"):
     net.run(d).free(); eng.sync()
