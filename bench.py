@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--gates", type=int, default=GATES_PER_STEP, help="gates per step per GPU (default 2^16, the BASELINE config)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-extra", action="store_true", help="skip the seconds/image side measurement")
-    ap.add_argument("--nets", default="mnist/sign1024x1,cifar/binarynet", help="nets timed for the seconds/image side measurement")
+    ap.add_argument("--nets", default="mnist/sign1024x1,mnist/relu1024x1,cifar/binarynet", help="nets timed for the seconds/image side measurement")
     return ap.parse_args()
 
 
@@ -338,7 +338,7 @@ def nets_seconds_per_image(eng, ks, client, dist, rank: int, world: int, names) 
         for name in names:
             spec = netspec.NETS[name]()
             label, px = netspec.load_image_csv(spec["image"])
-            ct = client.encrypt_image(px, ks.lwe_key, seed=7)
+            ct = client.encrypt(netspec.map_pixels(spec, px) * client.UNIT, ks.lwe_key, client.SECALPHA, 7)
             net = nets.EncryptedNet(eng, spec)
             net.build_tables(rank, world)                     # weights/tables on the device before the timed window (as prep() does)
             d = eng.upload(ct)

@@ -93,10 +93,16 @@ class EncryptedNet:
         return x
 
     def _layer_sharded(self, i: int, x: LweArray, dist) -> LweArray:
+        import os
+        import time
         import torch
         td, rank, world = dist
         info = self.layer_info(i)
+        dbg = os.environ.get("RS_SHARD_TIMES") and rank == 0
+        t0 = time.perf_counter()
         y, c0, c1 = self.layer_forward(i, x, rank, world)
+        if dbg:
+            self.eng.sync(); t1 = time.perf_counter()
         pixel_sharded = c1 - c0 == info["channels"] and y.count * world == info["out_count"]
         if c1 - c0 == info["channels"] and not pixel_sharded:
             return y                                   # layer not shardable: computed replicated on every rank
@@ -107,6 +113,8 @@ class EncryptedNet:
         gathered = torch.empty(world * words, dtype=torch.int32, device=dev)
         td.all_gather_into_tensor(gathered, local)     # NCCL over NVLink: the exchange step between layers
         torch.cuda.current_stream(dev).synchronize()
+        if dbg:
+            print(f"  layer {i}: forward {1e3*(t1-t0):.2f} ms, all-gather of {gathered.numel()*4/1e6:.1f} MB {1e3*(time.perf_counter()-t1):.2f} ms")
         out = self.eng.alloc(world * y.count)
         if pixel_sharded:                              # conv-less input layer: rank blocks of pixel rows are already canonical
             pixels, c_local, parts = world * y.count // info["channels"], info["channels"], 1

@@ -24,3 +24,11 @@ for k, n in enumerate(kinds):
 print(f"sum of kernels {tot:.2f} ms, wall {dt*1e3:.2f} ms, bootstraps {net.bootstraps()} -> {net.bootstraps()/dt:.0f}/s")
 for i in range(net.num_layers):
     print(i, net.layer_info(i))
+# per layer: host wall clock (sync after the layer) against the sum of its kernels
+x = d
+for i in range(net.num_layers):
+    eng.sync(); eng.profile_reset()
+    t0 = time.perf_counter(); y, _, _ = net.layer_forward(i, x); eng.sync(); dt = time.perf_counter() - t0
+    ks_ms = [eng.profile_get(k)[0] for k in range(4)]
+    print(f"layer {i}: wall {dt*1e3:9.2f} ms, kernels {sum(ks_ms):9.2f} ms (blind rotate {ks_ms[0]:.2f}, keyswitch {ks_ms[1]:.2f}, linear {ks_ms[2]:.2f}), host gap {dt*1e3-sum(ks_ms):7.2f} ms")
+    x = y

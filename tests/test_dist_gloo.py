@@ -36,8 +36,17 @@ def _worker(rank, world, port, tmpdir):
     cat = torch.cat(gathered).numpy().astype(np.uint32)       # [world][pixels][c_local]
     out = cat[nets.interleave_index(64, c1 - c0, world)]
     ok = np.array_equal(out, full)
-    # a non-shardable layer (3 channels, no conv stage) is replicated
+    # a conv-less input layer (3 channels) keeps its full channel range: it is sharded by output pixel instead, and the
+    # all-gather of the per-rank row blocks [pixels/world][channels] is already in canonical (h,w,c) order
     ok = ok and nets.shard_range(3, False, rank, world) == (0, 3)
+    L0 = layers[0]
+    full0 = LO.enc_linear(L0, ct)                            # [(h,w,c)][351], 64 pixels x 3 channels
+    per = 64 // world
+    mine0 = full0.reshape(64, 3, 351)[rank * per:(rank + 1) * per].reshape(-1, 351).copy()
+    g0 = [torch.empty(mine0.shape, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(g0, torch.from_numpy(mine0.astype(np.int64)))
+    cat0 = torch.cat(g0).numpy().astype(np.uint32)
+    ok = ok and np.array_equal(cat0[nets.interleave_index(64, 3, 1)], full0)
     flag = torch.tensor([int(ok)])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
