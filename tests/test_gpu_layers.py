@@ -38,6 +38,47 @@ def test_lincomb_kernel_bit_exact(oracle, engine):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_linear_stage_random_geometries_bit_exact(oracle, engine, tmp_path, seed):
+    """Conv / sum-pool index logic (lib/BinFunc.cpp:87-104,348-404, lib/IntFunc.cpp:598-634) on random geometries: window 1/3/5,
+    stride 1/2, same and valid padding, odd image sizes, ragged channel tiles (depth not a multiple of 16), Int and Bin
+    conventions, with and without a sum-pool.  One bootstrap-free layer (activation none) on random uint32 rows; integer
+    arithmetic mod 2^32, so the GPU rows must equal the oracle's exactly.  Also checks a 2-way channel shard of the same layer."""
+    from oracle import layers_oracle as LO
+    nets = _nets()
+    rng = np.random.default_rng(100 + seed)
+    h, w, dep = int(rng.integers(5, 12)), int(rng.integers(5, 12)), int(rng.integers(1, 6))
+    win = int(rng.choice([1, 3, 5])); stride = int(rng.choice([1, 2])); same = bool(rng.integers(0, 2))
+    if not same and min(h, w) - 2 * ((win - 1) // 2) < stride:
+        same = True
+    pool = str(rng.choice(["none", "sum"]))
+    layer = netspec._layer(str(rng.choice(["int", "bin"])), "conv", int(rng.choice([3, 16, 20, 34])), pool, "none",
+                           conv_win=(win, win), conv_stride=(stride, stride), conv_same_pad=same,
+                           pool_win=(2, 2), pool_stride=(2, 2), pool_same_pad=bool(rng.integers(0, 2)))
+    spec = dict(name=f"test/geom{seed}", input=(h, w, dep), layers=[layer], weights=None, image=None)
+    try:
+        spec["weights"] = netspec.write_random_weights(spec, str(tmp_path / "w.dat"), seed=seed, p_zero=0.3, bias_range=50)
+        layers = LO.prepare(spec, spec["weights"])
+    except (AssertionError, ValueError):
+        pytest.skip("degenerate geometry (empty output)")
+    if min(layers[0].q_dims) < 1:
+        pytest.skip("degenerate geometry (empty output)")
+    ct = rng.integers(0, 2 ** 32, size=(h * w * dep, 351), dtype=np.uint64).astype(np.uint32)
+    want = LO.enc_linear(layers[0], ct)
+    net = nets.EncryptedNet(engine, spec)
+    x = engine.upload(ct)
+    y, c0, c1 = net.layer_forward(0, x)
+    assert (c0, c1) == (0, layer["depth"])
+    assert np.array_equal(engine.download(y), want), spec
+    if layer["depth"] % 2 == 0:
+        cl = layer["depth"] // 2
+        for r in range(2):
+            part, p0, p1 = net.layer_forward(0, x, r, 2)
+            assert (p0, p1) == (r * cl, (r + 1) * cl)
+            assert np.array_equal(engine.download(part), want.reshape(-1, layer["depth"], 351)[:, p0:p1].reshape(-1, 351))
+    net.close()
+
+
 @pytest.mark.parametrize("name,nboot", [("mnist/sign1024x1", 1220), ("mnist/sign1024x3", 3268)])
 def test_mnist_sign_layers_bit_exact_and_scores(oracle, keyset, engine, name, nboot):
     from oracle import layers_oracle as LO

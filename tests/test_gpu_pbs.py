@@ -64,6 +64,20 @@ def test_pbs_bit_exact_and_decrypts(oracle, keyset, engine, count):
     assert np.array_equal(dec, np.where(bits == 1, 1, -1))
 
 
+def test_unbinarize_mu_and_empty_batch(oracle, keyset, engine):
+    """BinOps::unbinarize_int is the same bootstrap with mu = 1/2048 (MULTIBIT_SPACE, lib/BinOps_enc.cpp:188-192, lib/Layer.h:35);
+    an empty batch is a no-op; in == out aliasing is allowed."""
+    mu = oracle.to_torus(1, 2048)
+    bits, ct = _rand_bits_ct(oracle, keyset, 11, 300 * MU4096, 2.0 ** -15, 55)
+    dev = engine.upload(ct)
+    got = engine.download(engine.pbs(dev, mu, out=dev))            # in place
+    assert np.array_equal(got, oracle.pbs(ct, mu, keyset))
+    assert np.array_equal(oracle.decrypt(got, keyset.lwe_key, 2048), np.where(bits == 1, 1, -1))
+    assert engine.lib.rs_pbs_batch(engine.ctx, dev.ptr, dev.ptr, 0, mu) == 0
+    assert engine.lib.rs_gate_batch(engine.ctx, 0, dev.ptr, dev.ptr, dev.ptr, 0, mu) == 0
+    assert np.array_equal(engine.download(dev), got)                # untouched by the empty calls
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2])
 def test_test_vector_bootstrap_bit_exact(oracle, keyset, engine, variant):
     """rs_pbs_lut_batch (row f4): per-ciphertext test vectors, ciphertext c uses table c % m.  Bit-exact vs the oracle and the
