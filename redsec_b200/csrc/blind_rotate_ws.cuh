@@ -58,6 +58,19 @@ __device__ __forceinline__ void err_stat(double x) {
 __device__ __forceinline__ void err_stat(double) {}
 #endif
 
+#ifndef RS_WS_OPP
+#define RS_WS_OPP 0      // opportunistic extra BSK look-ahead of the front warps (slabs), see the producer duty below.
+                         // Measured with 1: 2^16 bootstraps 914.6 ms instead of 865 (the extra barrier test per row costs
+                         // more than the earlier request gains), so it is off; kept as a knob (RS_NVCC_EXTRA=-DRS_WS_OPP=1)
+#endif
+
+#ifndef RS_WS_REFILL
+#define RS_WS_REFILL 0   // 0: front warps claim and request slabs (default); 1: the back warp that consumes a BSK stage last
+                         // refills it (no producer duty in the front warps, copies requested 5 rows ahead).  Measured with 1:
+                         // one wave 8.33 ms instead of 7.96, 2^16 bootstraps 915 ms instead of 865 -- the shared-memory atomic whose
+                         // result decides who refills puts a round trip at the end of every back-warp row; kept as a knob
+#endif
+
 template <int STAGES, int XSLOTS>
 struct WsSmem {
     static constexpr int kCts = 4;
@@ -72,8 +85,9 @@ struct WsSmem {
     // barriers (8 B each): bsk_full[STAGES], bsk_empty[STAGES], x_full[4][XSLOTS], x_empty[4][XSLOTS], acc_ready[4][2]
     static constexpr int kBskFull = 0, kBskEmpty = STAGES, kXFull = 2 * STAGES, kXEmpty = kXFull + kCts * XSLOTS,
                          kAccReady = kXEmpty + kCts * XSLOTS, kNumBars = kAccReady + 2 * kCts;   // acc_ready[4][2]: one per accumulator polynomial
-    static constexpr int kIssuedOff = kBarOff + kNumBars * 8;
-    static constexpr int kTotal = kIssuedOff + 8;
+    static constexpr int kIssuedOff = kBarOff + kNumBars * 8;   // int issued; int consumed[STAGES] (RS_WS_REFILL)
+    static constexpr int kTotal = kIssuedOff + 8 + 4 * 8;
+    static_assert(STAGES <= 8, "consumed[] holds 8 counters");
     static_assert(kCtBytes % 16 == 0, "ciphertext block must stay 16-byte aligned");
     static_assert(XSLOTS >= 3, "the inverse holds one slot; the front warp needs two more to run ahead");
 };
@@ -124,6 +138,14 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *issued = 0;
+#if RS_WS_REFILL
+        for (int s = 0; s < STAGES; s++) {        // initial fill of the ring; afterwards the last consumer of a stage refills it
+            issued[2 + s] = 0;
+            mbar_arrive_expect_tx(bar_base + (S::kBskFull + s) * 8, S::kStageBytes);
+            tma_load_1d(smem_base + S::kStagesOff + s * S::kStageBytes, reinterpret_cast<const uint8_t*>(bsk_f) + (size_t)s * S::kStageBytes,
+                        S::kStageBytes, bar_base + (S::kBskFull + s) * 8);
+        }
+#endif
     }
     __syncthreads();
 
@@ -179,11 +201,19 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 WSP(1);
 #pragma unroll 1
                 for (int p = 0; p < BK_L; p++) {
+#if !RS_WS_REFILL
                     // ---- BSK producer duty (claimed in order by whichever front warp gets here first)
                     if (lane == 0) {
                         const int want = min(rowc + AHEAD, kTotalRows - 1);
+                        // slabs up to `want` are requested unconditionally (waiting for the ring stage if need be: STAGES > AHEAD +
+                        // XSLOTS makes that wait finite); up to RS_WS_OPP slabs beyond it are requested early when their stage
+                        // happens to be free already, which gives the bulk copy more time to land before the back warps need it
+                        const int opp = min(rowc + AHEAD + RS_WS_OPP, kTotalRows - 1);
                         int cur = *reinterpret_cast<volatile int*>(issued);
-                        while (cur <= want) {
+                        while (cur <= opp) {
+                            if (cur > want && cur >= STAGES &&
+                                !mbar_test(bar_base + (S::kBskEmpty + cur % STAGES) * 8, ((cur - STAGES) / STAGES) & 1))
+                                break;
                             const int prev = atomicCAS(issued, cur, cur + 1);
                             if (prev == cur) {
                                 const int ns = cur % STAGES;
@@ -202,6 +232,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                             }
                         }
                     }
+#endif
                     __syncwarp();
                     WSP(2);
                     // ---- ring slot: wait until both back warps have read its previous occupant
@@ -306,7 +337,25 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 if (x < 7) { b0 = n0; b1 = n1; }
             }
             __syncwarp();
+#if RS_WS_REFILL
+            // the warp that consumes this stage LAST (of the 2*active back warps) requests the slab STAGES rows ahead into it:
+            // the copy gets the longest possible head start and the front warps carry no producer duty
+            if (lane == 0) {
+                const int done = atomicAdd(issued + 2 + s, 1) + 1;
+                if (done % (2 * active) == 0) {
+                    const int next = rowc + STAGES;
+                    if (next < kTotalRows) {
+                        const uint32_t full = bar_base + (S::kBskFull + s) * 8;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(bsk_f) + (size_t)next * S::kStageBytes;
+                        mbar_arrive_expect_tx(full, S::kStageBytes);
+                        if (l2_keep > 0.f) tma_load_1d_hint(smem_base + S::kStagesOff + s * S::kStageBytes, src, S::kStageBytes, full, l2_policy_evict_last(l2_keep));
+                        else tma_load_1d(smem_base + S::kStagesOff + s * S::kStageBytes, src, S::kStageBytes, full);
+                    }
+                }
+            }
+#else
             if (lane == 0) mbar_arrive(bar_base + (S::kBskEmpty + s) * 8);
+#endif
             rowc++;
             WSP(3);
         }
