@@ -15,7 +15,7 @@ spec = netspec.NETS[name]()
 ks = client.keygen(0)
 eng = rs.Engine(local); eng.load_eval_key(ks.bsk, ks.ksk)
 label, px = netspec.load_image_csv(spec["image"])
-ct = client.encrypt_image(px, ks.lwe_key, seed=7)
+ct = client.encrypt(netspec.map_pixels(spec, px) * client.UNIT, ks.lwe_key, client.SECALPHA, 7)
 net = nets.EncryptedNet(eng, spec)
 net.build_tables(rank, world)
 d = eng.upload(ct)
