@@ -64,6 +64,29 @@ def test_pbs_bit_exact_and_decrypts(oracle, keyset, engine, count):
     assert np.array_equal(dec, np.where(bits == 1, 1, -1))
 
 
+def test_pbs_random_and_degenerate_ciphertexts_bit_exact(oracle, keyset, engine):
+    """3 000 arbitrary LWE rows (uniform random words, not encryptions: every mod-switched value occurs, including ~500
+    coefficients that round to 0 and skip their blind-rotate step) plus degenerate rows: trivial samples (a = 0) at phases 0,
+    1/2, +-3/4096 and -1/4096 (exactly half a slot below 0: rounds to slot 0, so +mu), an all-ones mask, and a mask whose every
+    coefficient rounds to 2N-1.  Bit-exact vs the oracle."""
+    rng = np.random.default_rng(77)
+    ct = rng.integers(0, 2 ** 32, size=(3000, 351), dtype=np.uint64).astype(np.uint32)
+    special = np.zeros((7, 351), np.uint32)
+    special[0, 350] = 0                       # trivial, phase exactly 0 -> +mu (SURVEY 8a)
+    special[1, 350] = 0x80000000              # trivial, phase 1/2
+    special[2, 350] = 3 * MU4096
+    special[3, 350] = (-3 * MU4096) & 0xFFFFFFFF
+    special[4, 350] = (-MU4096) & 0xFFFFFFFF  # -1/4096 = -half a slot: modSwitch rounds it to slot 0
+    special[5, :] = 0xFFFFFFFF                # every coefficient rounds to 0 mod 2N (wraps)
+    special[6, :350] = 0xFFE00000 - (1 << 20)  # rounds to 2N-1
+    ct = np.concatenate([special, ct])
+    got = engine.download(engine.pbs(engine.upload(ct), MU4096))
+    want = oracle.pbs(ct, MU4096, keyset)
+    assert np.array_equal(got, want)
+    dec = oracle.decrypt(got[:5], keyset.lwe_key, 4096)
+    assert list(dec) == [1, -1, 1, -1, 1]
+
+
 def test_unbinarize_mu_and_empty_batch(oracle, keyset, engine):
     """BinOps::unbinarize_int is the same bootstrap with mu = 1/2048 (MULTIBIT_SPACE, lib/BinOps_enc.cpp:188-192, lib/Layer.h:35);
     an empty batch is a no-op; in == out aliasing is allowed."""
