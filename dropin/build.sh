@@ -36,5 +36,8 @@ for net in $NETS; do
     $NVCC $CCBIN -c -o net_gpu.o net.cu $JOIN_FLAGS_GPU -lredcufhe -Xcompiler -fopenmp -Xcompiler -Wall -Xcompiler -DGPU_ENC
     $NVCC $CCBIN -c -o main_gpu.o main.cu $JOIN_FLAGS_GPU -lredcufhe -Xcompiler -fopenmp -Xcompiler -Wall -Xcompiler -DGPU_ENC
     $NVCC $CCBIN -o gpu-encrypt.out $LIB_DIR/GPU/*.o net_gpu.o main_gpu.o $JOIN_FLAGS_GPU -lredcufhe -lredsec_b200 -Xcompiler -fopenmp -Xcompiler -Wall -Xcompiler -DGPU_ENC )
+  # the source symlinks were only needed while compiling: drop them so that nothing under the repo resolves to reference code
+  rm -f "$T/nets/$net/main.cu" "$T/nets/$net/net.cu" "$T/nets/$net/net.cuh" "$T/nets/$net/net.h"
   echo "built $T/nets/$net/gpu-encrypt.out"
 done
+find "$T/nets" -maxdepth 2 -name '*.h' -type l -delete
