@@ -61,6 +61,7 @@ struct rs_ctx {
     uint64_t launches = 0;
     int br_variant = 0;
     int ks_variant = 0;
+    bool ws_split = true;         // row-split modes of the warp-specialised kernel for batches below 2 ciphertexts per SM (RS_WS_SPLIT=0 disables)
     float l2_keep = 0.45f;        // fraction of the BSK stream hinted L2 evict_last (RS_L2_KEEP; measured optimum)
 };
 
@@ -170,9 +171,12 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
         return fail(ctx, RS_ERR_STATE, "test-vector bootstraps are not implemented in the tensor-memory variants (rs_set_tuning 3/4)");
     constexpr int G = 4;
     const int grid = (int)((count + G - 1) / G);
-    // warp-specialised kernels partition the batch evenly over the grid; a batch below one wave (the 196-neuron MNIST layer)
-    // is spread over all SMs at 1-2 ciphertexts per CTA: a wave with <= 2 ciphertexts per SM takes 6.1 ms instead of 7.9
-    const int bgrid = count < (size_t)G * ctx->sm_count ? (int)std::min<size_t>(count, (size_t)ctx->sm_count) : grid;
+    // warp-specialised kernel: a batch below two ciphertexts per SM is latency-bound (one ciphertext alone on an SM needs 6.1 ms),
+    // so it is spread over all SMs and each ciphertext over 2 or 4 of the CTA's slots (row-split modes, blind_rotate_ws.cuh);
+    // larger batches below one wave are spread at <= 4 ciphertexts per CTA; full waves use ceil(count/4) CTAs of 4
+    const size_t sms = (size_t)ctx->sm_count;
+    const int split = !ctx->ws_split ? 1 : count <= sms ? 4 : count <= 2 * sms ? 2 : 1;
+    const int bgrid = count < (size_t)G * sms ? (int)std::min<size_t>(count, sms) : grid;
     {
         LaunchScope ls(ctx, RS_K_BLIND_ROTATE);
         if (ctx->br_variant == 3)
@@ -180,8 +184,14 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
                 in, (int)count, mu, ctx->bsk_f, ext);
         else if (ctx->br_variant == 4)
             rs::blind_rotate_tm_kernel<4, 3, 120, 184><<<grid, 512, rs::TmSmem<5, 3>::kTotal, ctx->stream>>>(in, (int)count, mu, ctx->bsk_f, ext);
+        else if (ctx->br_variant == 0 && split == 4)
+            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 4><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
+                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);
+        else if (ctx->br_variant == 0 && split == 2)
+            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
+                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);
         else if (ctx->br_variant == 0)
-            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
+            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 1><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
                 in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);
         else if (ctx->br_variant == 1) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext, lut, lut_mod);
         else br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext, lut, lut_mod);
@@ -277,7 +287,13 @@ int rs_ctx_create(rs_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             rs::WsSmem<kWsStages, kWsSlots>::kTotal);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 rs::WsSmem<kWsStages, kWsSlots>::kTotal);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              rs::WsSmem<kWsStages, kWsSlots>::kTotal);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(rs::blind_rotate_tm_kernel<5, 3, 120, 184>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -291,6 +307,7 @@ int rs_ctx_create(rs_ctx** out, int device) {
     if (e == cudaSuccess) e = br_prepare<4, 4>();
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
     if (const char* env = getenv("RS_L2_KEEP")) { float v = (float)atof(env); if (v >= 0.f && v <= 1.f) ctx->l2_keep = v; }
+    if (const char* env = getenv("RS_WS_SPLIT")) ctx->ws_split = atoi(env) != 0;
     if (ctx->l2_keep > 0.f)   // the evict_last hint only holds lines inside the persisting carve-out (82.9 MB max on B200); best effort
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
     if (const char* env = getenv("RS_KS_VARIANT")) { int v = atoi(env); if (v == 0 || v == 1) ctx->ks_variant = v; }

@@ -23,6 +23,13 @@
 //     grow to 192.  The pool is what the launch allocated (384*168 = 64512 registers, not the 65536 of the SM):
 //     8*32*192 + 4*32*120 = 64512.  (Asking for more blocks setmaxnreg.inc forever.)
 //
+// Row-split mode (SPLIT = 2 or 4) for batches below one / two ciphertexts per SM, which are latency-bound (a ciphertext alone on an
+// SM needs 6.1 ms: 7 000 rows one after the other): the 4 slots of a CTA then hold 4/SPLIT ciphertexts, and the SPLIT slots of a
+// ciphertext take its rows r = k (mod SPLIT) of every step, each with its own front warp, back-warp pair, exchange ring and partial
+// Fourier accumulators.  After the rows of a step the partial sums meet in shared memory, part 0 adds them and runs the inverse
+// transforms.  The summation order differs from the un-split kernel, the result does not: the inverse transform is rounded to the
+// exact integer convolution either way (pre-rounding error ~1e-3 against the 0.5 bound), so ciphertexts stay bit-identical.
+//
 // See fft512.cuh for the transform algebra; the arithmetic per row is identical to blind_rotate_kernel, so results are
 // bit-identical (tests/test_gpu_pbs.py::test_variants_agree).
 #pragma once
@@ -58,19 +65,6 @@ __device__ __forceinline__ void err_stat(double x) {
 __device__ __forceinline__ void err_stat(double) {}
 #endif
 
-#ifndef RS_WS_OPP
-#define RS_WS_OPP 0      // opportunistic extra BSK look-ahead of the front warps (slabs), see the producer duty below.
-                         // Measured with 1: 2^16 bootstraps 914.6 ms instead of 865 (the extra barrier test per row costs
-                         // more than the earlier request gains), so it is off; kept as a knob (RS_NVCC_EXTRA=-DRS_WS_OPP=1)
-#endif
-
-#ifndef RS_WS_REFILL
-#define RS_WS_REFILL 0   // 0: front warps claim and request slabs (default); 1: the back warp that consumes a BSK stage last
-                         // refills it (no producer duty in the front warps, copies requested 5 rows ahead).  Measured with 1:
-                         // one wave 8.33 ms instead of 7.96, 2^16 bootstraps 915 ms instead of 865 -- the shared-memory atomic whose
-                         // result decides who refills puts a round trip at the end of every back-warp row; kept as a knob
-#endif
-
 template <int STAGES, int XSLOTS>
 struct WsSmem {
     static constexpr int kCts = 4;
@@ -85,9 +79,8 @@ struct WsSmem {
     // barriers (8 B each): bsk_full[STAGES], bsk_empty[STAGES], x_full[4][XSLOTS], x_empty[4][XSLOTS], acc_ready[4][2]
     static constexpr int kBskFull = 0, kBskEmpty = STAGES, kXFull = 2 * STAGES, kXEmpty = kXFull + kCts * XSLOTS,
                          kAccReady = kXEmpty + kCts * XSLOTS, kNumBars = kAccReady + 2 * kCts;   // acc_ready[4][2]: one per accumulator polynomial
-    static constexpr int kIssuedOff = kBarOff + kNumBars * 8;   // int issued; int consumed[STAGES] (RS_WS_REFILL)
-    static constexpr int kTotal = kIssuedOff + 8 + 4 * 8;
-    static_assert(STAGES <= 8, "consumed[] holds 8 counters");
+    static constexpr int kIssuedOff = kBarOff + kNumBars * 8;
+    static constexpr int kTotal = kIssuedOff + 8;
     static_assert(kCtBytes % 16 == 0, "ciphertext block must stay 16-byte aligned");
     static_assert(XSLOTS >= 3, "the inverse holds one slot; the front warp needs two more to run ahead");
 };
@@ -97,7 +90,7 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 template <int N_REGS>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N_REGS)); }
 
-template <int STAGES, int XSLOTS>
+template <int STAGES, int XSLOTS, int SPLIT>
 __global__ void __launch_bounds__(384, 1)
 blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRIDE]
                        int count, uint32_t mu,
@@ -108,8 +101,10 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                        int lut_mod)                             // nullptr: the constant test vector mu of the sign bootstrap
 {
     using S = WsSmem<STAGES, XSLOTS>;
-    constexpr int AHEAD = 1;                       // a front warp starting row r makes sure slabs <= r+AHEAD are requested
+    static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "a ciphertext is spread over 1, 2 or 4 slots");
+    constexpr int AHEAD = 1;                       // a front warp starting the row of slab g makes sure slabs <= g+AHEAD are requested
     constexpr int kTotalRows = LWE_N * BK_ROWS;
+    constexpr int kRowsPerPart = BK_ROWS / SPLIT;  // rows a slot handles per blind-rotate step
     static_assert(STAGES > AHEAD + XSLOTS, "BSK ring must cover the front-to-back distance");
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
@@ -117,16 +112,16 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     int* issued = reinterpret_cast<int*>(smem + S::kIssuedOff);
 
     // balanced partition: CTA b owns ciphertexts [b*count/grid, (b+1)*count/grid): 4 each (fewer in the last CTAs) for the
-    // usual grid of ceil(count/4), 1-2 each when the host spreads a batch smaller than one wave over all SMs
+    // usual grid of ceil(count/4); at most 4/SPLIT each in the row-split modes, where the host spreads a small batch over all SMs
     const int first_ct = (int)((long long)blockIdx.x * count / gridDim.x);
-    const int active = (int)((long long)(blockIdx.x + 1) * count / gridDim.x) - first_ct;
+    const int active = (int)((long long)(blockIdx.x + 1) * count / gridDim.x) - first_ct;   // ciphertexts of this CTA
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(bar_base + (S::kBskFull + s) * 8, 1);
-            mbar_init(bar_base + (S::kBskEmpty + s) * 8, active * 2);      // one arrival per back warp
+            mbar_init(bar_base + (S::kBskEmpty + s) * 8, active * 2);      // one arrival per back warp that consumes the slab
         }
         for (int j = 0; j < S::kCts; j++) {
             for (int x = 0; x < XSLOTS; x++) {
@@ -138,46 +133,44 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *issued = 0;
-#if RS_WS_REFILL
-        for (int s = 0; s < STAGES; s++) {        // initial fill of the ring; afterwards the last consumer of a stage refills it
-            issued[2 + s] = 0;
-            mbar_arrive_expect_tx(bar_base + (S::kBskFull + s) * 8, S::kStageBytes);
-            tma_load_1d(smem_base + S::kStagesOff + s * S::kStageBytes, reinterpret_cast<const uint8_t*>(bsk_f) + (size_t)s * S::kStageBytes,
-                        S::kStageBytes, bar_base + (S::kBskFull + s) * 8);
-        }
-#endif
     }
     __syncthreads();
 
     if (warp >= 8) {
         // =========================================================================================== FRONT warp
         reg_dealloc<120>();
-        const int j = warp - 8;
-        if (j >= active) return;
-        const int ct = first_ct + j;
+        const int j = warp - 8;            // slot
+        const int jc = j / SPLIT;          // ciphertext of this CTA the slot works for
+        const int part = j % SPLIT;        // rows r = part (mod SPLIT) of every step
+        if (jc >= active) return;
+        const int ct = first_ct + jc;
         uint8_t* cbase = smem + S::kCtOff + j * S::kCtBytes;
-        uint32_t* acc = reinterpret_cast<uint32_t*>(cbase);
+        uint8_t* pbase = smem + S::kCtOff + (jc * SPLIT) * S::kCtBytes;      // part 0's slot holds the accumulator
+        uint32_t* acc = reinterpret_cast<uint32_t*>(pbase);
         uint16_t* bara = reinterpret_cast<uint16_t*>(cbase + S::kAccBytes);
         double2* ring = reinterpret_cast<double2*>(cbase + S::kAccBytes + S::kBaraBytes);
         const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
-        const uint32_t accready = bar_base + (S::kAccReady + 2 * j) * 8;   // [2]: per accumulator polynomial
+        const uint32_t accready = bar_base + (S::kAccReady + 2 * (jc * SPLIT)) * 8;   // [2]: per accumulator polynomial
         const uint8_t* bsk_bytes = reinterpret_cast<const uint8_t*>(bsk_f);
         const uint64_t l2pol = l2_policy_evict_last(l2_keep);
 
         // ---- modswitch and accumulator init (step 2)
         const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
         for (int i = lane; i < LWE_N; i += 32) bara[i] = (uint16_t)modswitch_2N(lwe[i]);
-        const int barb = (int)modswitch_2N(lwe[LWE_N]);
-        const uint32_t* tv = lut ? lut + (size_t)(ct % lut_mod) * N : nullptr;
-        for (int k = lane; k < N; k += 32) {
-            acc[k] = 0;
-            const int idx = (k + barb) & (2 * N - 1);                        // X^{2N-barb} * testvector
-            const uint32_t v = tv ? tv[idx & (N - 1)] : mu;                  // (mu + mu X + ... for the sign bootstrap)
-            acc[N + k] = idx < N ? v : 0u - v;
+        if (part == 0) {
+            const int barb = (int)modswitch_2N(lwe[LWE_N]);
+            const uint32_t* tv = lut ? lut + (size_t)(ct % lut_mod) * N : nullptr;
+            for (int k = lane; k < N; k += 32) {
+                acc[k] = 0;
+                const int idx = (k + barb) & (2 * N - 1);                        // X^{2N-barb} * testvector
+                const uint32_t v = tv ? tv[idx & (N - 1)] : mu;                  // (mu + mu X + ... for the sign bootstrap)
+                acc[N + k] = idx < N ? v : 0u - v;
+            }
         }
         __syncwarp();
+        if (SPLIT > 1) asm volatile("bar.sync %0, %1;" ::"r"(8 + jc), "n"(32 * SPLIT) : "memory");   // the ciphertext's front warps: acc is initialised
 
-        int rowc = 0;    // rows produced by this front warp (= BSK slab index of the row)
+        int rowc = 0;    // rows produced by this front warp (SPLIT == 1: also the BSK slab index of the row)
         WSP_DECL;
 #pragma unroll 1
         for (int i = 0; i < LWE_N; i++) {
@@ -201,19 +194,13 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 WSP(1);
 #pragma unroll 1
                 for (int p = 0; p < BK_L; p++) {
-#if !RS_WS_REFILL
+                    if (SPLIT > 1 && ((c * BK_L + p) % SPLIT) != part) continue;      // another slot's row
+                    const int slab = SPLIT > 1 ? i * BK_ROWS + c * BK_L + p : rowc;     // BSK slab of this row
                     // ---- BSK producer duty (claimed in order by whichever front warp gets here first)
                     if (lane == 0) {
-                        const int want = min(rowc + AHEAD, kTotalRows - 1);
-                        // slabs up to `want` are requested unconditionally (waiting for the ring stage if need be: STAGES > AHEAD +
-                        // XSLOTS makes that wait finite); up to RS_WS_OPP slabs beyond it are requested early when their stage
-                        // happens to be free already, which gives the bulk copy more time to land before the back warps need it
-                        const int opp = min(rowc + AHEAD + RS_WS_OPP, kTotalRows - 1);
+                        const int want = min(slab + AHEAD, kTotalRows - 1);
                         int cur = *reinterpret_cast<volatile int*>(issued);
-                        while (cur <= opp) {
-                            if (cur > want && cur >= STAGES &&
-                                !mbar_test(bar_base + (S::kBskEmpty + cur % STAGES) * 8, ((cur - STAGES) / STAGES) & 1))
-                                break;
+                        while (cur <= want) {
                             const int prev = atomicCAS(issued, cur, cur + 1);
                             if (prev == cur) {
                                 const int ns = cur % STAGES;
@@ -232,7 +219,6 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                             }
                         }
                     }
-#endif
                     __syncwarp();
                     WSP(2);
                     // ---- ring slot: wait until both back warps have read its previous occupant
@@ -261,6 +247,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             }
         }
         WSP_FLUSH();
+        if (part != 0) return;
         mbar_wait_warp_long(accready, (LWE_N - 1) & 1);     // the last step's accumulator update, both polynomials
         mbar_wait_warp_long(accready + 8, (LWE_N - 1) & 1);
         // ---- sample extract: a'[0]=acc_a[0], a'[k]=-acc_a[N-k], b'=acc_b[0]
@@ -272,19 +259,22 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
 
     // =============================================================================================== BACK warp
     reg_alloc<192>();
-    const int j = warp >> 1;
-    if (j >= active) return;
+    const int j = warp >> 1;               // slot
+    const int jc = j / SPLIT;
+    const int part = j % SPLIT;
+    if (jc >= active) return;
     const int u = lane + 32 * (warp & 1);      // thread-column of the 64-wide transform layout
     const int lo = u & 7, rr = u >> 3;
     uint8_t* cbase = smem + S::kCtOff + j * S::kCtBytes;
+    uint8_t* pbase = smem + S::kCtOff + (jc * SPLIT) * S::kCtBytes;
     double2* ring = reinterpret_cast<double2*>(cbase + S::kAccBytes + S::kBaraBytes);
     const uint32_t xfull = bar_base + (S::kXFull + j * XSLOTS) * 8, xempty = bar_base + (S::kXEmpty + j * XSLOTS) * 8;
-    const uint32_t accready = bar_base + (S::kAccReady + 2 * j) * 8;   // [2]: per accumulator polynomial
-    uint32_t* acc = reinterpret_cast<uint32_t*>(cbase);
+    const uint32_t accready = bar_base + (S::kAccReady + 2 * (jc * SPLIT)) * 8;   // [2]: per accumulator polynomial
+    uint32_t* acc = reinterpret_cast<uint32_t*>(pbase);
     Twiddles tw;
     make_twiddles(tw, u);
 
-    int rowc = 0;
+    int rowc = 0;               // rows consumed by this warp
     uint32_t row_ready = 0;     // non-blocking test of the NEXT row's exchange slot, issued one row early (see below)
     WSP_DECL;
 #pragma unroll 1
@@ -293,11 +283,12 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
 #pragma unroll
         for (int x = 0; x < 8; x++) { f0[x] = make_double2(0.0, 0.0); f1[x] = make_double2(0.0, 0.0); }
 #pragma unroll 1
-        for (int row = 0; row < 2 * BK_L; row++) {
+        for (int row = 0; row < kRowsPerPart; row++) {
             const int slot = rowc % XSLOTS;
-            const int s = rowc % STAGES;
+            const int slab = SPLIT > 1 ? i * BK_ROWS + row * SPLIT + part : rowc;    // this slot's row r = row*SPLIT + part of step i
+            const int s = slab % STAGES;
             // test the slab's barrier now and consume the answer after the transform (mbarrier round trip off the critical path)
-            const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1));
+            const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + (S::kBskFull + s) * 8, (slab / STAGES) & 1));
             // the row's exchange slot was tested before the previous row's MAC; only a miss pays the mbarrier round trip here
             WSP(7);
             if (!__all_sync(0xffffffffu, row_ready)) mbar_wait_warp_long(xfull + slot * 8, (rowc / XSLOTS) & 1);
@@ -310,7 +301,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             __syncwarp();
             // the row has been consumed into registers.  The LAST row of a step keeps its slot: the inverse transforms below use it
             // as their exchange buffer and release it afterwards, so the front warp can refill the other slots meanwhile
-            if (lane == 0 && row != 2 * BK_L - 1) mbar_arrive(xempty + slot * 8);
+            if (lane == 0 && row != kRowsPerPart - 1) mbar_arrive(xempty + slot * 8);
             rotate_exchange(v, lo);
             // the first BSK operands are requested before pass 3 when the slab is already resident (the common case), so that
             // their shared-memory latency overlaps the butterflies instead of stalling the first FMA of the MAC
@@ -321,7 +312,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
 
             WSP(1);
             if (!slab_ready) {
-                mbar_wait_warp(bar_base + (S::kBskFull + s) * 8, (rowc / STAGES) & 1);
+                mbar_wait_warp(bar_base + (S::kBskFull + s) * 8, (slab / STAGES) & 1);
                 b0 = B[0]; b1 = B[NH];
             }
             WSP(2);
@@ -337,25 +328,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 if (x < 7) { b0 = n0; b1 = n1; }
             }
             __syncwarp();
-#if RS_WS_REFILL
-            // the warp that consumes this stage LAST (of the 2*active back warps) requests the slab STAGES rows ahead into it:
-            // the copy gets the longest possible head start and the front warps carry no producer duty
-            if (lane == 0) {
-                const int done = atomicAdd(issued + 2 + s, 1) + 1;
-                if (done % (2 * active) == 0) {
-                    const int next = rowc + STAGES;
-                    if (next < kTotalRows) {
-                        const uint32_t full = bar_base + (S::kBskFull + s) * 8;
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(bsk_f) + (size_t)next * S::kStageBytes;
-                        mbar_arrive_expect_tx(full, S::kStageBytes);
-                        if (l2_keep > 0.f) tma_load_1d_hint(smem_base + S::kStagesOff + s * S::kStageBytes, src, S::kStageBytes, full, l2_policy_evict_last(l2_keep));
-                        else tma_load_1d(smem_base + S::kStagesOff + s * S::kStageBytes, src, S::kStageBytes, full);
-                    }
-                }
-            }
-#else
             if (lane == 0) mbar_arrive(bar_base + (S::kBskEmpty + s) * 8);
-#endif
             rowc++;
             WSP(3);
         }
@@ -364,6 +337,34 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         // has not released yet.  Polynomial 0 is finished and published first (acc_ready[0]) so that the front warp produces
         // the next step's first rows into the two free slots while polynomial 1 is still being transformed.
         double2* ibuf = ring + ((rowc - 1) % XSLOTS) * FFT_BUF;
+        if (SPLIT > 1) {
+            // Row-split: the slots of a ciphertext hold partial sums.  Parts 1.. park theirs in the held slot (polynomial 0) and the
+            // slot before it (polynomial 1: its row was released, and the front warp cannot refill it before it has seen
+            // acc_ready[0], which part 0 signals only after it has read the partial sums), then meet part 0 at a named barrier.
+            double2* pbuf1 = ring + ((rowc - 2 + XSLOTS) % XSLOTS) * FFT_BUF;
+            group_sync(j);      // both back warps of the slot are done reading the step's forward rows
+            if (part != 0) {
+#pragma unroll
+                for (int x = 0; x < 8; x++) { ibuf[x * 64 + u] = f0[x]; pbuf1[x * 64 + u] = f1[x]; }
+                __threadfence_block();
+                asm volatile("bar.arrive %0, %1;" ::"r"(12 + jc), "n"(64 * SPLIT) : "memory");
+                // the held slot is released by part 0's accumulator update below: acc_ready orders the front warp's refill
+                if (lane == 0) mbar_arrive(xempty + ((rowc - 1) % XSLOTS) * 8);
+                continue;
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(12 + jc), "n"(64 * SPLIT) : "memory");
+#pragma unroll 1
+            for (int k = 1; k < SPLIT; k++) {
+                const double2* oring = reinterpret_cast<const double2*>(cbase + k * S::kCtBytes + S::kAccBytes + S::kBaraBytes);
+                const double2* o0 = oring + ((rowc - 1) % XSLOTS) * FFT_BUF;      // every part has consumed the same number of rows
+                const double2* o1 = oring + ((rowc - 2 + XSLOTS) % XSLOTS) * FFT_BUF;
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
+                    const double2 a0 = o0[x * 64 + u], a1 = o1[x * 64 + u];
+                    f0[x].x += a0.x; f0[x].y += a0.y; f1[x].x += a1.x; f1[x].y += a1.y;
+                }
+            }
+        }
         auto inverse_poly = [&](double2 (&f)[8], int poly) {
             group_sync(j);      // both back warps are done reading ibuf (the last forward row / the previous polynomial)
             dft8<+1>(f);
