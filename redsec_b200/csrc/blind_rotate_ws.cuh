@@ -26,8 +26,8 @@
 // Row-split mode (SPLIT = 2 or 4) for batches below one / two ciphertexts per SM, which are latency-bound (a ciphertext alone on an
 // SM needs 6.1 ms: 7 000 rows one after the other): the 4 slots of a CTA then hold 4/SPLIT ciphertexts, and the SPLIT slots of a
 // ciphertext take its rows r = k (mod SPLIT) of every step, each with its own front warp, back-warp pair, exchange ring and partial
-// Fourier accumulators.  After the rows of a step the partial sums meet in shared memory, part 0 adds them and runs the inverse
-// transforms.  The summation order differs from the un-split kernel, the result does not: the inverse transform is rounded to the
+// Fourier accumulators.  After the rows of a step the partial sums meet in shared memory; part 0 adds up polynomial 0 and part 1
+// polynomial 1 and each runs one inverse transform.  The summation order differs from the un-split kernel, the result does not: the inverse transform is rounded to the
 // exact integer convolution either way (pre-rounding error ~1e-3 against the 0.5 bound), so ciphertexts stay bit-identical.
 //
 // See fft512.cuh for the transform algebra; the arithmetic per row is identical to blind_rotate_kernel, so results are
@@ -338,30 +338,39 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         // the next step's first rows into the two free slots while polynomial 1 is still being transformed.
         double2* ibuf = ring + ((rowc - 1) % XSLOTS) * FFT_BUF;
         if (SPLIT > 1) {
-            // Row-split: the slots of a ciphertext hold partial sums.  Parts 1.. park theirs in the held slot (polynomial 0) and the
-            // slot before it (polynomial 1: its row was released, and the front warp cannot refill it before it has seen
-            // acc_ready[0], which part 0 signals only after it has read the partial sums), then meet part 0 at a named barrier.
-            double2* pbuf1 = ring + ((rowc - 2 + XSLOTS) % XSLOTS) * FFT_BUF;
+            // Row-split: the slots of a ciphertext hold partial sums.  Part 0 owns polynomial 0 and part 1 polynomial 1 (both inverse
+            // transforms run at the same time).  Every part parks the partial sums it does not own in its own ring: polynomial 1
+            // (polynomial 0 for part 1) in the slot BEFORE the held one -- that row was released, but the front warp cannot refill it
+            // before it has seen acc_ready, which the owners signal only after both have read every partial sum -- and, for parts
+            // 2 and 3, polynomial 0 in the held slot.  Then the parts meet the two owners at a named barrier.
+            double2* pbuf = ring + ((rowc - 2 + XSLOTS) % XSLOTS) * FFT_BUF;
             group_sync(j);      // both back warps of the slot are done reading the step's forward rows
-            if (part != 0) {
 #pragma unroll
-                for (int x = 0; x < 8; x++) { ibuf[x * 64 + u] = f0[x]; pbuf1[x * 64 + u] = f1[x]; }
-                __threadfence_block();
+            for (int x = 0; x < 8; x++) {
+                if (part != 1) pbuf[x * 64 + u] = f1[x]; else pbuf[x * 64 + u] = f0[x];
+                if (part >= 2) ibuf[x * 64 + u] = f0[x];
+            }
+            __threadfence_block();
+            if (part >= 2) {
                 asm volatile("bar.arrive %0, %1;" ::"r"(12 + jc), "n"(64 * SPLIT) : "memory");
-                // the held slot is released by part 0's accumulator update below: acc_ready orders the front warp's refill
-                if (lane == 0) mbar_arrive(xempty + ((rowc - 1) % XSLOTS) * 8);
+                if (lane == 0) mbar_arrive(xempty + ((rowc - 1) % XSLOTS) * 8);   // refills are ordered by acc_ready (see above)
                 continue;
             }
             asm volatile("bar.sync %0, %1;" ::"r"(12 + jc), "n"(64 * SPLIT) : "memory");
+            const int hslot = (rowc - 1) % XSLOTS, pslot = (rowc - 2 + XSLOTS) % XSLOTS;   // every part has consumed the same number of rows
 #pragma unroll 1
-            for (int k = 1; k < SPLIT; k++) {
-                const double2* oring = reinterpret_cast<const double2*>(cbase + k * S::kCtBytes + S::kAccBytes + S::kBaraBytes);
-                const double2* o0 = oring + ((rowc - 1) % XSLOTS) * FFT_BUF;      // every part has consumed the same number of rows
-                const double2* o1 = oring + ((rowc - 2 + XSLOTS) % XSLOTS) * FFT_BUF;
+            for (int k = 0; k < SPLIT; k++) {
+                if (k == part) continue;
+                const double2* oring = reinterpret_cast<const double2*>(pbase + k * S::kCtBytes + S::kAccBytes + S::kBaraBytes);
+                // part 0 collects polynomial 0: parked in the pslot of part 1, in the held slot of parts 2, 3;
+                // part 1 collects polynomial 1: parked in the pslot of every other part
+                const double2* o = oring + ((part == 0 && k >= 2) ? hslot : pslot) * FFT_BUF;
+                if (part == 0) {
 #pragma unroll
-                for (int x = 0; x < 8; x++) {
-                    const double2 a0 = o0[x * 64 + u], a1 = o1[x * 64 + u];
-                    f0[x].x += a0.x; f0[x].y += a0.y; f1[x].x += a1.x; f1[x].y += a1.y;
+                    for (int x = 0; x < 8; x++) { const double2 t = o[x * 64 + u]; f0[x].x += t.x; f0[x].y += t.y; }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 8; x++) { const double2 t = o[x * 64 + u]; f1[x].x += t.x; f1[x].y += t.y; }
                 }
             }
         }
@@ -394,10 +403,18 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 acc[poly * N + u + 64 * q + NH] += (uint32_t)__double2ll_rn(v[q].y);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(accready + poly * 8);
+            if (SPLIT == 1 && lane == 0) mbar_arrive(accready + poly * 8);
         };
-        inverse_poly(f0, 0);
-        inverse_poly(f1, 1);
+        if (SPLIT == 1) {
+            inverse_poly(f0, 0);
+            inverse_poly(f1, 1);
+        } else {
+            if (part == 0) inverse_poly(f0, 0); else inverse_poly(f1, 1);
+            // both owners have read every parked partial sum and updated their accumulator polynomial: only now may the front warps
+            // of the ciphertext refill the rings
+            asm volatile("bar.sync %0, %1;" ::"r"(14 + jc), "n"(128) : "memory");
+            if (lane == 0) mbar_arrive(accready + part * 8);
+        }
         if (lane == 0) mbar_arrive(xempty + ((rowc - 1) % XSLOTS) * 8);    // the last row's slot, held for the inverse exchange
         WSP(4);
     }
