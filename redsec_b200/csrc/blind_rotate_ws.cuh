@@ -23,8 +23,8 @@
 //     grow to 192.  The pool is what the launch allocated (384*168 = 64512 registers, not the 65536 of the SM):
 //     8*32*192 + 4*32*120 = 64512.  (Asking for more blocks setmaxnreg.inc forever.)
 //
-// Row-split mode (SPLIT = 2 or 4) for batches below one / two ciphertexts per SM, which are latency-bound (a ciphertext alone on an
-// SM needs 6.1 ms: 7 000 rows one after the other): the 4 slots of a CTA then hold 4/SPLIT ciphertexts, and the SPLIT slots of a
+// Row-split mode (SPLIT = 2; 4 exists but is slower, see api.cu) for batches below two ciphertexts per SM, which are latency-bound
+// (a ciphertext alone on an SM needs 6.1 ms: 7 000 rows one after the other): the 4 slots of a CTA then hold up to 4/SPLIT ciphertexts, and the SPLIT slots of a
 // ciphertext take its rows r = k (mod SPLIT) of every step, each with its own front warp, back-warp pair, exchange ring and partial
 // Fourier accumulators.  After the rows of a step the partial sums meet in shared memory; part 0 adds up polynomial 0 and part 1
 // polynomial 1 and each runs one inverse transform.  The summation order differs from the un-split kernel, the result does not: the inverse transform is rounded to the
