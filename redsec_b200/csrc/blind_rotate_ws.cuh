@@ -102,7 +102,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
 {
     using S = WsSmem<STAGES, XSLOTS>;
     static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "a ciphertext is spread over 1, 2 or 4 slots");
-    constexpr int AHEAD = 1;                       // a front warp starting the row of slab g makes sure slabs <= g+AHEAD are requested
+    constexpr int AHEAD = 1;                       // a front warp that has produced the row of slab g makes sure slabs <= g+AHEAD+1 are requested
     constexpr int kTotalRows = LWE_N * BK_ROWS;
     constexpr int kRowsPerPart = BK_ROWS / SPLIT;  // rows a slot handles per blind-rotate step
     static_assert(STAGES > AHEAD + XSLOTS, "BSK ring must cover the front-to-back distance");
@@ -170,6 +170,36 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         __syncwarp();
         if (SPLIT > 1) asm volatile("bar.sync %0, %1;" ::"r"(8 + jc), "n"(32 * SPLIT) : "memory");   // the ciphertext's front warps: acc is initialised
 
+        // ---- BSK producer duty: slabs are claimed in order by whichever front warp gets here first.  It runs at the END of a row,
+        // after the row has been handed to the back warps: the claim is a chain of shared-memory round trips (counter, CAS, stage
+        // barrier, expect_tx, bulk copy) of ~700 cycles that would otherwise delay every row by as much
+        auto request_slabs = [&](int upto) {
+            if (lane == 0) {
+                const int want = min(upto, kTotalRows - 1);
+                int cur = *reinterpret_cast<volatile int*>(issued);
+                while (cur <= want) {
+                    const int prev = atomicCAS(issued, cur, cur + 1);
+                    if (prev == cur) {
+                        const int ns = cur % STAGES;
+                        if (cur >= STAGES)
+                            mbar_wait_thread(bar_base + (S::kBskEmpty + ns) * 8, ((cur - STAGES) / STAGES) & 1);
+                        mbar_arrive_expect_tx(bar_base + (S::kBskFull + ns) * 8, S::kStageBytes);
+                        if (l2_keep > 0.f)
+                            tma_load_1d_hint(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
+                                             S::kStageBytes, bar_base + (S::kBskFull + ns) * 8, l2pol);
+                        else
+                            tma_load_1d(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
+                                        S::kStageBytes, bar_base + (S::kBskFull + ns) * 8);
+                        cur++;
+                    } else {
+                        cur = prev;
+                    }
+                }
+            }
+            __syncwarp();
+        };
+        request_slabs(part + AHEAD);     // the first row's slab (and its successor) before the pipeline starts
+
         int rowc = 0;    // rows produced by this front warp (SPLIT == 1: also the BSK slab index of the row)
         WSP_DECL;
 #pragma unroll 1
@@ -196,30 +226,6 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 for (int p = 0; p < BK_L; p++) {
                     if (SPLIT > 1 && ((c * BK_L + p) % SPLIT) != part) continue;      // another slot's row
                     const int slab = SPLIT > 1 ? i * BK_ROWS + c * BK_L + p : rowc;     // BSK slab of this row
-                    // ---- BSK producer duty (claimed in order by whichever front warp gets here first)
-                    if (lane == 0) {
-                        const int want = min(slab + AHEAD, kTotalRows - 1);
-                        int cur = *reinterpret_cast<volatile int*>(issued);
-                        while (cur <= want) {
-                            const int prev = atomicCAS(issued, cur, cur + 1);
-                            if (prev == cur) {
-                                const int ns = cur % STAGES;
-                                if (cur >= STAGES)
-                                    mbar_wait_thread(bar_base + (S::kBskEmpty + ns) * 8, ((cur - STAGES) / STAGES) & 1);
-                                mbar_arrive_expect_tx(bar_base + (S::kBskFull + ns) * 8, S::kStageBytes);
-                                if (l2_keep > 0.f)
-                                    tma_load_1d_hint(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
-                                                     S::kStageBytes, bar_base + (S::kBskFull + ns) * 8, l2pol);
-                                else
-                                    tma_load_1d(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
-                                                S::kStageBytes, bar_base + (S::kBskFull + ns) * 8);
-                                cur++;
-                            } else {
-                                cur = prev;
-                            }
-                        }
-                    }
-                    __syncwarp();
                     WSP(2);
                     // ---- ring slot: wait until both back warps have read its previous occupant
                     const int slot = rowc % XSLOTS;
@@ -243,6 +249,8 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                     if (lane == 0) mbar_arrive(xfull + slot * 8);
                     rowc++;
                     WSP(4);
+                    request_slabs(slab + AHEAD + 1);      // the next row's slab and the one after it
+                    WSP(2);
                 }
             }
         }
