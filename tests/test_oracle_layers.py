@@ -87,3 +87,15 @@ def test_relu_test_vectors_reproduce_the_staircase():
         assert sat.sum() > 100
         wide = np.abs(xs) < 1536
         assert np.array_equal(got[sat][:, wide], want[sat][:, wide])
+
+
+def test_relu_weight_file_size_identity():
+    """SURVEY.md 5.4 with the slope block of a ReLU+BN layer: relu1024x1 = bias(1+4) + [tern(1+196*1024*2/8) + bias(1+4096) +
+    slope(1+4096)] + [tern(1+1024*10*2/8) + bias(1+40)] bytes, and prepare() consumes the file exactly."""
+    from oracle import layers_oracle as LO
+    spec = netspec.NETS["mnist/relu1024x1"]()
+    assert os.path.getsize(spec["weights"]) == 5 + (1 + 50176) + 2 * (1 + 4096) + (1 + 2560) + (1 + 40) == 60978
+    layers = LO.prepare(spec, spec["weights"])
+    assert [L.q_dims for L in layers] == [(14, 14, 1), (1, 1, 1024), (1, 1, 10)]
+    assert layers[1].slope is not None and layers[1].slope.min() > 0 and layers[1].twin_conv and not layers[0].twin_conv
+    assert netspec.map_pixels(spec, [0, 99, 100, 199, 200, 255]).tolist() == [-1, -1, 0, 0, 1, 1]
