@@ -10,8 +10,9 @@
 //   * warpgroup 2 = 4 FRONT warps, one per ciphertext.  A front warp owns the torus32 accumulator (shared memory): per
 //     blind-rotate step it forms (X^a - 1)*acc, gadget-decomposes it, and for each of the 20 (polynomial, level) rows
 //     runs pass 1 of the forward transform (twist + radix-8) for all 64 thread-columns (two halves of 32) and writes the
-//     result into a 3-slot exchange ring.  It also claims and requests BSK slabs (TMA).  It is the lighter role on
-//     purpose: the ring stays full and the back warps, which carry the FP64 bulk, never wait for it.
+//     result into a 3-slot exchange ring.  After handing a row over it claims and requests BSK slabs (TMA) -- at the END of
+//     the row, because the claim is ~700 cycles of dependent shared-memory round trips that must not delay the hand-over.
+//     It is the lighter role on purpose: the ring stays full and the back warps, which carry the FP64 bulk, rarely wait.
 //   * warpgroups 0,1 = 8 BACK warps, two per ciphertext.  A back warp reads a row from the exchange ring, runs passes 2
 //     and 3 (twiddles fused as FMAs, exchange 2 through shuffles), multiplies by the BSK slab and accumulates in
 //     registers (Fourier accumulators, 64 registers).  After 20 rows the pair runs both inverse transforms (their
@@ -23,12 +24,14 @@
 //     grow to 192.  The pool is what the launch allocated (384*168 = 64512 registers, not the 65536 of the SM):
 //     8*32*192 + 4*32*120 = 64512.  (Asking for more blocks setmaxnreg.inc forever.)
 //
-// Row-split mode (SPLIT = 2; 4 exists but is slower, see api.cu) for batches below two ciphertexts per SM, which are latency-bound
-// (a ciphertext alone on an SM needs 6.1 ms: 7 000 rows one after the other): the 4 slots of a CTA then hold up to 4/SPLIT ciphertexts, and the SPLIT slots of a
-// ciphertext take its rows r = k (mod SPLIT) of every step, each with its own front warp, back-warp pair, exchange ring and partial
-// Fourier accumulators.  After the rows of a step the partial sums meet in shared memory; part 0 adds up polynomial 0 and part 1
-// polynomial 1 and each runs one inverse transform.  The summation order differs from the un-split kernel, the result does not: the inverse transform is rounded to the
-// exact integer convolution either way (pre-rounding error ~1e-3 against the 0.5 bound), so ciphertexts stay bit-identical.
+// Row-split mode (SPLIT = 2; 4 exists but is slower, see api.cu) for batches below two ciphertexts per SM, which are
+// latency-bound (a ciphertext alone on an SM needs 6.1 ms un-split: 7 000 rows one after the other): the 4 slots of a CTA
+// then hold up to 4/SPLIT ciphertexts, and the SPLIT slots of a ciphertext take its rows r = k (mod SPLIT) of every step,
+// each with its own front warp, back-warp pair, exchange ring and partial Fourier accumulators.  After the rows of a step
+// the partial sums meet in shared memory; part 0 adds up polynomial 0 and part 1 polynomial 1 and each runs one inverse
+// transform.  The summation order differs from the un-split kernel, the result does not: the inverse transform is rounded
+// to the exact integer convolution either way (pre-rounding error ~1e-3 against the 0.5 bound), so ciphertexts stay
+// bit-identical (tests/test_gpu_pbs.py compares counts 1..300 with the oracle: split 2 up to 296, un-split above).
 //
 // See fft512.cuh for the transform algebra; the arithmetic per row is identical to blind_rotate_kernel, so results are
 // bit-identical (tests/test_gpu_pbs.py::test_variants_agree).
