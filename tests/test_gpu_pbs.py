@@ -52,7 +52,7 @@ def test_keyswitch_tiled_matches_untiled_at_scale(engine, keyset):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("count", [1, 5, 6, 7, 300])
+@pytest.mark.parametrize("count", [1, 5, 6, 7, 200, 300])
 def test_pbs_bit_exact_and_decrypts(oracle, keyset, engine, count):
     O = oracle
     # inputs +-200/4096: far enough from 0 that the modswitch noise (sigma ~ 7.7/4096) cannot flip the sign
