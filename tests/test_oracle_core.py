@@ -98,3 +98,46 @@ def test_test_vector_bootstrap_exact_fft_and_slot_semantics(oracle, keyset):
     assert len(set(slot // 1024)) == 2                   # both halves of the torus were exercised
     const = np.full((1, 1024), LO.UNIT, dtype=np.uint32)
     assert np.array_equal(O.pbs_lut(ct[:3], const, keyset), O.pbs(ct[:3], LO.UNIT, keyset))
+
+
+def test_one_blind_rotate_step_against_numpy(oracle, keyset):
+    """Independent restatement of ONE blind-rotate step in numpy int64: an LWE sample whose mask has a single
+    non-zero coefficient runs exactly one external product.  Pins the rotation direction (acc = X^{-barb} tv, then
+    acc += BK_i (.) ((X^{a_i} - 1) acc)), the gadget decomposition (offset, digits in [-4, 3], level p <-> 2^{32-3(p+1)}), the row
+    order of the bootstrapping key (row = c*l + p, two output polynomials) and the negacyclic product, for both oracle variants."""
+    O = oracle
+    N, l = 1024, 10
+    rng = np.random.default_rng(3)
+    mu = 0x00100000
+    for i, a_i, b in [(7, 0x12345678, 0x9ABCDEF0), (349, 0xFFD00000, 0x00000000), (0, 0x80000000, 0x7FFFFFFF)]:
+        lwe = np.zeros(351, np.uint32)
+        lwe[i], lwe[350] = a_i, b
+        ms = lambda x: ((int(x) + (1 << 20)) >> 21) % (2 * N)            # modSwitchFromTorus32(x, 2N)
+        bara, barb = ms(a_i), ms(b)
+        assert bara != 0
+
+        def mul_x(poly, k):                                              # X^k * poly mod X^N + 1, k in [0, 2N)
+            out = np.zeros(N, np.int64)
+            for j in range(N):
+                t = j + k
+                s = -1 if (t // N) % 2 else 1
+                out[t % N] = s * poly[j]
+            return out
+        tv = np.full(N, mu, np.int64)
+        acc = [np.zeros(N, np.int64), mul_x(tv, (2 * N - barb) % (2 * N))]
+        off = sum(4 << (32 - 3 * p) for p in range(1, l + 1)) & 0xFFFFFFFF
+        res = [np.zeros(N, np.int64), np.zeros(N, np.int64)]
+        bsk = np.asarray(keyset.bsk, dtype=np.uint32).reshape(350, 2 * l, 2, N)
+        for c in range(2):
+            tmp = ((mul_x(acc[c], bara) - acc[c]) + off) & 0xFFFFFFFF
+            for p in range(l):
+                d = ((tmp >> (32 - 3 * (p + 1))) & 7) - 4
+                for co in range(2):
+                    B = bsk[i, c * l + p, co].astype(np.int32).astype(np.int64)     # signed representative: same product mod 2^32
+                    full = np.convolve(d, B)                                      # exact in int64 (|d| <= 4, |B| < 2^31, 1024 terms)
+                    neg = full[:N].copy()
+                    neg[:N - 1] -= full[N:]
+                    res[co] += neg
+        want = np.concatenate([(acc[0] + res[0]) & 0xFFFFFFFF, (acc[1] + res[1]) & 0xFFFFFFFF]).astype(np.uint32)
+        assert np.array_equal(O.blind_rotate(lwe, mu, keyset, exact=True), want), (i, "exact")
+        assert np.array_equal(O.blind_rotate(lwe, mu, keyset, exact=False), want), (i, "fft")
