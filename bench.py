@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--gates", type=int, default=GATES_PER_STEP, help="gates per step per GPU (default 2^16, the BASELINE config)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-extra", action="store_true", help="skip the seconds/image side measurement")
-    ap.add_argument("--nets", default="mnist/sign1024x1,mnist/relu1024x1,cifar/binarynet", help="nets timed for the seconds/image side measurement")
+    ap.add_argument("--nets", default="mnist/sign1024x1,mnist/sign1024x2,mnist/sign1024x3,mnist/cnn_builder,mnist/relu1024x1,cifar/binarynet",
+                    help="nets timed for the seconds/image side measurement (BASELINE configs 1, 3, 4, 5 + one ReLU net)")
+    ap.add_argument("--images", type=int, default=3, help="timed images per net (median reported), after one untimed warm-up image")
     return ap.parse_args()
 
 
@@ -103,52 +105,81 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline(ks, a, b, target_seconds: float, check_against=None) -> dict:
-    """Oracle port of the TFHE gate bootstrap on the host cores (bounded sample of the same workload)."""
+def probe_upstream_tfhe() -> dict:
+    """look for an installed upstream TFHE (libtfhe-spqlios-fma) on this box.  If it were present
+    the CPU arm could bind it; it is not part of the image (no network), so this records the probe and the arm stays the port."""
+    import ctypes.util
+    found = None
+    for name in ("tfhe-spqlios-fma", "tfhe-spqlios-avx", "tfhe-nayuki-portable"):
+        path = ctypes.util.find_library(name)
+        if path:
+            found = path
+            break
+    if not found:
+        try:
+            out = subprocess.run(["ldconfig", "-p"], capture_output=True, text=True, timeout=10).stdout
+            hits = [l.split("=>")[-1].strip() for l in out.splitlines() if "tfhe" in l.lower()]
+            found = hits[0] if hits else None
+        except Exception:
+            found = None
+    return {"libtfhe_found": found,
+            "note": ("upstream TFHE is installed; the CPU arm still times the oracle port (no binding written: its key/ciphertext "
+                     "layouts are unverifiable here)") if found else
+                    "upstream TFHE v1.1 (libtfhe-spqlios-fma) is not installed on this box; the CPU arm is the oracle port"}
+
+
+def cpu_baseline(ks, a, b, target_seconds: float, op: str = "NAND", check_against=None) -> dict:
+    """Oracle port of the TFHE gate bootstrap on the host cores (bounded sample of the same workload).  `op` is the gate the GPU
+    ran LAST, so the sample's ciphertexts can be compared with the timed batch's (sample_bit_exact_vs_gpu)."""
     from oracle import oracle as O
     oks = O.KeySet(ks.lwe_key, ks.tlwe_key, ks.bsk, ks.ksk)
     _ = oks.bsk_fft
     threads = host_threads()
     mu = 1 << 29
     t0 = time.perf_counter()
-    O.gate("NAND", a[: 2 * threads], b[: 2 * threads], mu, oks, threads=threads)
+    O.gate(op, a[: 2 * threads], b[: 2 * threads], mu, oks, threads=threads)
     probe = time.perf_counter() - t0
     n = int(max(4 * threads, min(a.shape[0], 2 * threads * target_seconds / max(probe, 1e-3))))
     n = (n // threads) * threads
     t0 = time.perf_counter()
-    out = O.gate("NAND", a[:n], b[:n], mu, oks, threads=threads)
+    out = O.gate(op, a[:n], b[:n], mu, oks, threads=threads)
     dt = time.perf_counter() - t0
     t1 = time.perf_counter()
-    O.gate("NAND", a[:2], b[:2], mu, oks, threads=1)
+    O.gate(op, a[:2], b[:2], mu, oks, threads=1)
     single = (time.perf_counter() - t1) / 2
     res = {"value": n / dt, "unit": "gates/s", "cores": threads, "kind": "port",
-           "sample": f"{n} NAND gates of the step's batch, oracle FFT port (not the upstream TFHE binary), omp parallel for over gates",
-           "ms_per_gate_single_core": single * 1e3}
+           "sample": f"{n} {op} gates of the step's batch, oracle FFT port (not the upstream TFHE binary), omp parallel for over gates",
+           "ms_per_gate_single_core": single * 1e3, "upstream_probe": probe_upstream_tfhe()}
     if check_against is not None:
         res["sample_bit_exact_vs_gpu"] = bool(np.array_equal(out, check_against[:n]))
+        res["sample_checked_gates"] = int(n)
     return res, n / dt
 
 
+def _oracle_bits(O, bits, lwe_key, seed):
+    mu = np.where(np.asarray(bits) == 1, 1 << 29, -(1 << 29))
+    return O.encrypt(mu, 2.0 ** -25, lwe_key, seed)
+
+
 def run_reference(args, rank: int):
-    """--impl reference: the CPU implementation of the path (oracle port) with all host threads, bounded sample per step."""
+    """--impl reference: the CPU implementation of the path (oracle port) with all host threads, bounded sample per step.
+    Keygen and encryption are the oracle's too: this arm never loads libredsec_b200.so."""
     if rank != 0:
         return
-    from redsec_b200 import client
     from oracle import oracle as O
-    ks = client.keygen(0)
-    oks = O.KeySet(ks.lwe_key, ks.tlwe_key, ks.bsk, ks.ksk)
+    oks = O.keygen(0)
     _ = oks.bsk_fft
     threads = host_threads()
     rng = np.random.default_rng(1)
     n = max(2 * threads, 16)
-    a = client.encrypt_bits(rng.integers(0, 2, n), ks.lwe_key, seed=11)
-    b = client.encrypt_bits(rng.integers(0, 2, n), ks.lwe_key, seed=12)
+    a = _oracle_bits(O, rng.integers(0, 2, n), oks.lwe_key, 11)
+    b = _oracle_bits(O, rng.integers(0, 2, n), oks.lwe_key, 12)
     t0 = time.perf_counter(); O.gate("NAND", a, b, 1 << 29, oks, threads=threads); probe = time.perf_counter() - t0
     budget = 150.0 / max(args.steps + args.warmup, 1)               # whole run within a few minutes
     per_step = int(max(threads, min(4096, n * min(budget, 20.0) / max(probe, 1e-3))))
     per_step = max(threads, (per_step // threads) * threads)
-    a = client.encrypt_bits(rng.integers(0, 2, per_step), ks.lwe_key, seed=13)
-    b = client.encrypt_bits(rng.integers(0, 2, per_step), ks.lwe_key, seed=14)
+    a = _oracle_bits(O, rng.integers(0, 2, per_step), oks.lwe_key, 13)
+    b = _oracle_bits(O, rng.integers(0, 2, per_step), oks.lwe_key, 14)
     for s in range(args.warmup):
         O.gate("NAND" if s % 2 == 0 else "XNOR", a, b, 1 << 29, oks, threads=threads)
     t0 = time.perf_counter()
@@ -161,8 +192,10 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": "bootstrapped_gates_per_sec", "value": value, "unit": "gates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_gates_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": "gates/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample_gates_per_step": per_step,
+                   "parity": "oracle parity unpinned vs upstream TFHE (no TFHE source or fixture in the reference tree)"},
+        "cpu_baseline": {"value": value, "unit": "gates/s", "cores": threads, "kind": "port", "sample": sample,
+                         "upstream_probe": probe_upstream_tfhe()},
         "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -250,7 +283,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         eng.gate_host(ops[s % 2], na, nb, mu, nout)
     barrier()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_verified = bool(np.array_equal(nout.view(np.uint32), out_dev)) if last_op == ops[(args.steps - 1) % 2] else None
+    e2e_verified = bool(np.array_equal(nout.view(np.uint32), out_dev))
 
     # max over ranks (device time)
     t = torch.tensor([ms, e2e_wall_ms], dtype=torch.float64, device=dev)
@@ -260,11 +293,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     extra = {}
     if not args.no_extra:
-        extra = nets_seconds_per_image(eng, ks, client, dist, rank, world, args.nets.split(","))
+        extra = nets_seconds_per_image(eng, ks, client, dist, rank, world, args.nets.split(","), args.images)
 
     cpu = None
     if rank == 0 and world >= 1:
-        cpu, _ = cpu_baseline(ks, a, b, args.cpu_seconds, check_against=(out_dev if last_op == "NAND" else None))
+        cpu, _ = cpu_baseline(ks, a, b, args.cpu_seconds, op=last_op, check_against=out_dev)
 
     if rank == 0:
         total_gates = world * G * args.steps
@@ -320,19 +353,24 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         }
         if extra:
             line["extra"] = {"encrypted_inference": extra, "n_gpus": world,
-                             "note": "one image, layers sharded by output channel across the GPUs, NCCL all-gather between layers"}
+                             "note": "seconds per image = median over timed images after one warm-up image; whole network in one library "
+                                     "call (rs_net_run), layers sharded by output channel across the GPUs, NCCL all-gather between layers "
+                                     "on the engine stream; device time, max over ranks"}
         print(json.dumps(line))
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
-def nets_seconds_per_image(eng, ks, client, dist, rank: int, world: int, names) -> dict:
-    """Side measurement (not the headline): encrypted inference seconds/image of the reference's nets on `world` GPUs,
-    activations resident, layers neuron-sharded by output channel with an NCCL all-gather between layers.
-    Every rank takes part; the time is the slowest rank's, bracketed by barrier + device sync on both sides."""
+def nets_seconds_per_image(eng, ks, client, dist, rank: int, world: int, names, images: int = 3) -> dict:
+    """Side measurement (BASELINE.json's second metric): encrypted inference seconds/image of the reference's nets on `world`
+    GPUs.  The whole network is ONE library call (rs_net_run): activations resident, layers neuron-sharded by output channel,
+    NCCL all-gather between layers issued by the library on the engine stream, no host synchronisation between layers.
+    Per net: one untimed warm-up image (fills the caching allocator and NCCL's buffers), then `images` timed images, each
+    bracketed by barrier + device sync on both sides and timed as the slowest rank's device time; the median is reported."""
     import torch
     out = {}
+    dev = torch.device("cuda", eng.device)
     try:
         from redsec_b200 import netspec, nets
         for name in names:
@@ -342,23 +380,39 @@ def nets_seconds_per_image(eng, ks, client, dist, rank: int, world: int, names) 
             net = nets.EncryptedNet(eng, spec)
             net.build_tables(rank, world)                     # weights/tables on the device before the timed window (as prep() does)
             d = eng.upload(ct)
-            distinfo = (dist, rank, world) if dist is not None else None
-            if name.startswith("mnist"):
-                net.run(d, dist=distinfo).free(); eng.sync()          # warm-up (cheap); CIFAR runs once, kernels are already warm
-            if dist is not None:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            res = net.run(d, dist=distinfo); eng.sync()
-            if dist is not None:
-                dist.barrier()
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
+            comm = net.comm_for((dist, rank, world) if dist is not None else None)
+
+            def barrier():
+                if dist is not None:
+                    dist.barrier()
+                torch.cuda.synchronize(dev)
+
+            net.run_native(d, comm).free()                    # warm-up image
+            eng.sync()
+            times, res = [], None
+            stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
+            for _ in range(max(1, images)):
+                if res is not None:
+                    res.free()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                res = net.run_native(d, comm)
+                e1.record(stream)
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+                if dist is not None:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                times.append(float(t[0]))
             scores = client.decrypt(eng.download(res), ks.lwe_key, 4096)
+            res.free()
+            dt = float(np.median(times))
             key = name.replace("/", "_")
-            out[key] = {"s_per_image": dt, "bootstraps": int(net.bootstraps()), "bootstraps_per_sec": net.bootstraps() / dt,
-                        "argmax": int(np.argmax(scores)), "label": int(label), "scores": [int(v) for v in scores]}
+            out[key] = {"s_per_image": dt, "s_per_image_all": times, "images_timed": len(times), "bootstraps": int(net.bootstraps()),
+                        "bootstraps_per_sec": net.bootstraps() / dt, "argmax": int(np.argmax(scores)), "label": int(label),
+                        "scores": [int(v) for v in scores]}
             net.close()
+            eng.pool_trim()
     except Exception as e:   # the side measurement must never break the headline line
         out["error"] = str(e)[:300]
     return out

@@ -49,10 +49,29 @@ typedef struct rs_ctx rs_ctx;
  * replaces redcufhe::SetGPUNum/Initialize(PubKey&) per device (nets/mnist/sign1024x1/net.cu:43-49),
  * redcufhe::CleanUp() (main.cu:84), Synchronize()/CuCheckError() (main.cu:74-75). */
 int rs_ctx_create(rs_ctx **out, int device);
+/* fails with RS_ERR_STATE while layer / net / communicator objects created on the context are still alive (they free their
+ * device tables through it): destroy those first.  Every entry point makes the context's device current for the duration of
+ * the call and restores the caller's, so one process may hold contexts on several devices.  Device-wide side effect of
+ * rs_ctx_create: it raises cudaLimitPersistingL2CacheSize to the device maximum (the BSK stream uses an L2 evict_last hint). */
 int rs_ctx_destroy(rs_ctx *ctx);
+int rs_ctx_retain(rs_ctx *ctx);                      /* taken by redsec::Layer / rs_net / rs_comm for their lifetime */
+int rs_ctx_release(rs_ctx *ctx);
+int rs_pool_trim(rs_ctx *ctx);                       /* return the caching allocator's parked blocks to the driver (syncs) */
 const char *rs_last_error(const rs_ctx *ctx);       /* ctx may be NULL: last creation error */
 int rs_set_stream(rs_ctx *ctx, void *cuda_stream);  /* adopt a caller-owned cudaStream_t (NULL = own stream) */
-int rs_sync(rs_ctx *ctx);
+int rs_get_stream(rs_ctx *ctx, void **cuda_stream); /* the cudaStream_t of the selected lane */
+int rs_ctx_device(const rs_ctx *ctx);
+int rs_sync(rs_ctx *ctx);                           /* waits for every lane */
+/* Lanes: extra streams with their own bootstrap scratch, for independent chains of launches that should overlap (the
+ * reference round-robins its per-ciphertext launches over 40 streams, lib/GPU/BinFunc_gpu.cu:116-138,599-621; here a lane
+ * carries whole batched launches).  Lane 0 is the context's stream.  rs_lane_select(k) routes the following calls to lane k;
+ * rs_lane_fork makes lanes 1.. wait for what lane 0 has issued so far, rs_lane_join makes lane 0 wait for lanes 1...
+ * Buffers shared between lanes must be allocated before the fork and freed after the join. */
+int rs_lanes(rs_ctx *ctx, int n);
+int rs_lane_count(const rs_ctx *ctx);
+int rs_lane_select(rs_ctx *ctx, int lane);
+int rs_lane_fork(rs_ctx *ctx);
+int rs_lane_join(rs_ctx *ctx);
 
 /* -- evaluation key: north-star item (c) -------------------------------------------------------------
  * replaces new_tfheGateBootstrappingCloudKeySet_fromFile -> bk->bkFFT (nets/mnist/sign1024x1/net.cpp:53-55)
@@ -66,6 +85,7 @@ int rs_lwe_alloc(rs_ctx *ctx, size_t count, uint32_t **dev_out);
 int rs_lwe_free(rs_ctx *ctx, uint32_t *dev);
 int rs_lwe_upload(rs_ctx *ctx, uint32_t *dev, const uint32_t *host_wire, size_t count);
 int rs_lwe_download(rs_ctx *ctx, uint32_t *host_wire, const uint32_t *dev, size_t count);
+int rs_lwe_copy(rs_ctx *ctx, uint32_t *dst_dev, const uint32_t *src_dev, size_t count);   /* device to device, stream ordered */
 int rs_host_alloc(void **out, size_t bytes);        /* pinned host memory for the *_host entry points */
 int rs_host_free(void *p);
 
@@ -127,6 +147,9 @@ int rs_lwe_conv(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *in_dev, const in
                 const uint32_t *bias_dev /* [out_dep] torus32, may be NULL */, const rs_conv_desc *desc);
 /* dev[c].b += value for every row (adds the trivial sample (0,value)); lweNoiselessTrivial + lweAddTo, lib/BinOps_enc.cpp:137-141 */
 int rs_lwe_add_const(rs_ctx *ctx, uint32_t *dev, size_t count, uint32_t value);
+/* dev[r].b += bias_dev[r % mod] (per-channel bias, rows channel-fastest): the bias add of {Bin,Int}Func::Quantize::execute /
+ * add_bias (lib/BinFunc.cpp:1063-1065,1085-1107) as a stage of its own for callers that compose Func objects */
+int rs_lwe_add_bias(rs_ctx *ctx, uint32_t *dev, size_t count, const uint32_t *bias_dev, int mod);
 int rs_dev_alloc(rs_ctx *ctx, size_t bytes, void **dev_out);
 int rs_dev_free(rs_ctx *ctx, void *dev);
 int rs_dev_upload(rs_ctx *ctx, void *dev, const void *host, size_t bytes);
@@ -135,6 +158,26 @@ int rs_dev_download(rs_ctx *ctx, void *host, const void *dev, size_t bytes);
 /* restore canonical (pixel, channel) order after an all-gather of per-rank channel slices:
  * in [world][pixels][c_local]  ->  out [pixels][world*c_local]   (SURVEY 8e exchange step) */
 int rs_lwe_interleave(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *gathered_dev, size_t pixels, int c_local, int world);
+
+/* -- exchange step between layers: NCCL all-gather of the ranks' output-channel blocks over NVLink, issued on the
+ * context's stream (no host synchronisation).  The reference has none: with NUM_GPUS > 1 (lib/GPU/Layer.cuh:15) each OpenMP
+ * thread fills only its own iterations of its own replica enc_segs[idx] (lib/GPU/BinFunc_gpu.cu:599-621) and nothing merges
+ * them.  NCCL is bound at run time (dlopen libnccl.so.2); a single-GPU caller never needs it.
+ *   rs_comm_init_rank: one process per GPU; rank 0 makes the id with rs_comm_unique_id and the caller distributes it
+ *   rs_comm_init_all : one process, n contexts on n devices (the reference's one-host-thread-per-GPU model); each host thread
+ *                      then drives its own context + communicator */
+#define RS_COMM_ID_BYTES 128
+typedef struct rs_comm rs_comm;
+int rs_comm_unique_id(uint8_t *id /*[RS_COMM_ID_BYTES]*/);
+int rs_comm_init_rank(rs_ctx *ctx, rs_comm **out, const uint8_t *id, int rank, int world);
+int rs_comm_init_all(rs_ctx **ctxs, int n, rs_comm **comms_out /*[n]*/);
+int rs_comm_destroy(rs_comm *comm);
+int rs_comm_rank(const rs_comm *comm);
+int rs_comm_world(const rs_comm *comm);
+rs_ctx *rs_comm_ctx(const rs_comm *comm);
+const char *rs_comm_last_error(void);
+/* out[world][rows_per_rank] <- every rank's in[rows_per_rank] (device rows of RS_LWE_STRIDE words) */
+int rs_allgather(rs_comm *comm, uint32_t *out_dev, const uint32_t *in_dev, size_t rows_per_rank);
 
 /* -- client side (host C++) ------------------------------------------------------------
  * replaces client/gen_secure_keyset.cpp:94-120, client/encrypt_image.cpp:65-85, client/decrypt_image.cpp:46-63 */
@@ -162,7 +205,7 @@ typedef struct rs_layer_params {    /* tNetParams, lib/Layer.h:126-167 */
 } rs_layer_params;
 /* neuron partition of one layer: output-channel block [ch_begin,ch_end) of `rank`; whole layer when not shardable */
 int rs_shard_range(int channels, int has_conv, int rank, int world, int *ch_begin, int *ch_end);
-rs_net *rs_net_create(rs_ctx *ctx);
+rs_net *rs_net_create(rs_ctx *ctx);     /* ctx may be NULL: a net that can be prepared and asked for shapes / shard plan, not run */
 void rs_net_destroy(rs_net *net);
 int rs_net_add_layer(rs_net *net, int int_layer, int conv_type, int out_depth, int pool_type, int quant_type,
                      const rs_layer_params *p);
@@ -180,6 +223,19 @@ int rs_net_layer_info(rs_net *net, int layer, size_t *out_count, int *channels, 
  * frees *out_dev with rs_lwe_free.  Output rows are [pixel][ch_begin..ch_end). */
 int rs_net_layer_forward(rs_net *net, int layer, const uint32_t *in_dev, size_t in_count, int rank, int world,
                          uint32_t **out_dev, size_t *out_count, int *ch_begin, int *ch_end);
+
+/* how layer `layer` is split over `world` ranks: *mode 0 = computed whole on every rank, 1 = output-channel blocks
+ * (all-gather + rs_lwe_interleave), 2 = output-pixel blocks (all-gather only); *rows_per_rank = ciphertexts each rank
+ * contributes to the all-gather; *c_local = channels per rank block.  Host logic only (works on a net created without ctx). */
+int rs_net_shard_plan(rs_net *net, int layer, int world, int *mode, size_t *rows_per_rank, int *c_local);
+/* one layer, neuron-sharded over the communicator (comm == NULL: whole layer on this GPU); does not consume in_dev */
+int rs_net_layer_forward_sharded(rs_net *net, int layer, rs_comm *comm, const uint32_t *in_dev, size_t in_count,
+                                 uint32_t **out_dev, size_t *out_count);
+/* HeBNN::run (nets/mnist/sign1024x1/net.cu:105-120) for the whole network on the engine stream.  comm == NULL: one GPU.  Otherwise every layer is
+ * neuron-sharded over the communicator's ranks (each GPU a full key replica, output channels partitioned) with an NCCL
+ * all-gather between layers and NO host synchronisation; every rank receives the full output.  Does not consume in_dev;
+ * the caller frees *out_dev with rs_lwe_free. */
+int rs_net_run(rs_net *net, rs_comm *comm, const uint32_t *in_dev, size_t in_count, uint32_t **out_dev, size_t *out_count);
 
 /* -- measurement ------------------------------------------------------------------------------------- */
 int rs_profile_enable(rs_ctx *ctx, int on);         /* bracket every kernel launch with CUDA events on the ctx stream */

@@ -327,6 +327,110 @@ def enc_linear(L, ct):
     return x.reshape(-1, O.LWE_WORDS)
 
 
+def enc_linear_rows(L, ct, idx):
+    """Rows `idx` (flat indices into the (h,w,c) pre-activation array) of enc_linear(L, ct), computed one output at a time
+    from the reference's index formulas (lib/BinFunc.cpp:228-310 window gather, lib/IntFunc.cpp:665-697 pooling) without
+    forming the whole layer: what the sampled full-size parity tests use (CIFAR conv2 is 53 G word-adds as a whole)."""
+    ls = L.spec
+    x = np.ascontiguousarray(ct, dtype=np.uint32)
+    W = O.LWE_WORDS
+    qh_, qw_, qd_ = L.q_dims
+    unit_b = np.zeros(W, dtype=np.uint32)
+    unit_b[O.n] = UNIT
+    if L.has_conv:
+        x = x.reshape(L.cin + (W,))
+        wh, ww, sh, sw, ofh, ofw, oh, ow = L.conv_geom
+        h, w, dep = L.cin
+        int_mode = ls["kind"] == "int" and not L.twin_conv
+    elif L.has_sumpool:
+        x = x.reshape(L.sp_in + (qd_, W))
+    else:
+        x = x.reshape(L.q_dims + (W,))
+
+    def conv_at(ph, pw, od):
+        if not L.has_conv:
+            return x[ph, pw, od]
+        acc = np.zeros(W, dtype=np.uint32)
+        extra = 0                                       # count of -1/4096 contributions (IntFunc zero weight / padding)
+        for fh in range(wh):
+            iy = fh + ph * sh - ofh
+            for fw in range(ww):
+                ix = fw + pw * sw - ofw
+                wv = L.weights[fh, fw, :, od].astype(np.int64)
+                if not (0 <= iy < h and 0 <= ix < w):
+                    if int_mode:
+                        extra += dep
+                    continue
+                v = x[iy, ix]                           # [dep][W]
+                pos, neg = wv == 1, wv == -1
+                acc += v[pos].sum(axis=0, dtype=np.uint32)
+                acc -= v[neg].sum(axis=0, dtype=np.uint32)
+                if int_mode:
+                    extra += int((wv == 0).sum())
+        with np.errstate(over="ignore"):
+            acc[O.n] -= np.uint32((extra * UNIT) & 0xFFFFFFFF)
+            if L.twin_conv:
+                acc[O.n] -= np.uint32((int(L.neg_count[od]) * UNIT) & 0xFFFFFFFF)
+        return acc
+
+    out = np.zeros((len(idx), W), dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        _rows_loop(L, idx, out, conv_at, unit_b)
+    return out
+
+
+def _rows_loop(L, idx, out, conv_at, unit_b):
+    ls = L.spec
+    W = O.LWE_WORDS
+    qh_, qw_, qd_ = L.q_dims
+    for k, flat in enumerate(np.asarray(idx, dtype=np.int64)):
+        c = int(flat % qd_); qw = int((flat // qd_) % qw_); qh = int(flat // (qd_ * qw_))
+        if L.has_sumpool:
+            ph_, pw_, sh2, sw2, ofh2, ofw2, oh2, ow2 = L.sp_geom
+            ih, iw = L.sp_in
+            acc = np.zeros(W, dtype=np.uint32)
+            for fh in range(ph_):
+                iy = qh * sh2 - ofh2 + fh
+                if not 0 <= iy < ih:
+                    continue
+                for fw in range(pw_):
+                    ix = qw * sw2 - ofw2 + fw
+                    if 0 <= ix < iw:
+                        acc += conv_at(iy, ix, c)
+        else:
+            acc = conv_at(qh, qw, c).copy()
+        if ls["act"] != "relu":
+            acc[O.n] += np.uint32((int(L.bias[c]) * UNIT) & 0xFFFFFFFF)
+        out[k] = acc
+
+
+def enc_layer_rows(L, ct, idx, ks, threads=0):
+    """Rows `idx` of enc_layer_forward(L, ct, ks): flat indices into the layer OUTPUT ((oh,ow,c) after a max-pool).  A pooled
+    output costs 4 sign bootstraps + 3 ORs, any other one bootstrap (none for an activation-free layer)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    if L.spec["act"] == "none":
+        return enc_linear_rows(L, ct, idx)
+    if L.spec["act"] == "relu":
+        lin = enc_linear_rows(L, ct, idx)
+        tv, half = relu_test_vectors(L)
+        # pbs_lut uses table c % len(luts) for ciphertext c: hand each sampled row its own channel's table
+        out = O.pbs_lut(lin, tv[idx % L.q_dims[2]], ks, threads=threads)
+        out[:, O.n] += np.uint32(half)
+        return out
+    if not L.has_maxpool:
+        return O.pbs(enc_linear_rows(L, ct, idx), UNIT, ks, threads=threads)
+    ph_, pw_, sh, sw, oh, ow = L.mp_geom
+    assert (ph_, pw_) == (2, 2), "oracle OR tree restated for the 2x2 windows the shipped nets use"
+    qh_, qw_, qd_ = L.q_dims
+    c = idx % qd_; b = (idx // qd_) % ow; a = idx // (qd_ * ow)
+    def q_index(fh, fw):
+        return ((a * sh + fh) * qw_ + (b * sw + fw)) * qd_ + c
+    bits = [O.pbs(enc_linear_rows(L, ct, q_index(fh, fw)), EIGHTH, ks, threads=threads) for fh in range(2) for fw in range(2)]
+    top = O.gate("OR", bits[0], bits[1], EIGHTH, ks, threads=threads)
+    bot = O.gate("OR", bits[2], bits[3], EIGHTH, ks, threads=threads)
+    return O.gate("OR", top, bot, UNIT, ks, threads=threads)
+
+
 def enc_layer_forward(L, ct, ks, threads=0):
     """One encrypted layer: linear part, one sign bootstrap per neuron, max-pool OR tree."""
     lin = enc_linear(L, ct)

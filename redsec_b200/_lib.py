@@ -16,6 +16,14 @@ vp = C.c_void_p
 SIGNATURES = {
     "rs_ctx_create": (C.c_int, [C.POINTER(vp), C.c_int]),
     "rs_ctx_destroy": (C.c_int, [vp]),
+    "rs_ctx_retain": (C.c_int, [vp]),
+    "rs_ctx_release": (C.c_int, [vp]),
+    "rs_pool_trim": (C.c_int, [vp]),
+    "rs_lanes": (C.c_int, [vp, C.c_int]),
+    "rs_lane_count": (C.c_int, [vp]),
+    "rs_lane_select": (C.c_int, [vp, C.c_int]),
+    "rs_lane_fork": (C.c_int, [vp]),
+    "rs_lane_join": (C.c_int, [vp]),
     "rs_last_error": (C.c_char_p, [vp]),
     "rs_set_stream": (C.c_int, [vp, vp]),
     "rs_sync": (C.c_int, [vp]),
@@ -24,6 +32,22 @@ SIGNATURES = {
     "rs_lwe_free": (C.c_int, [vp, vp]),
     "rs_lwe_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "rs_lwe_download": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_lwe_copy": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_lwe_add_bias": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_int]),
+    "rs_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
+    "rs_ctx_device": (C.c_int, [vp]),
+    "rs_comm_unique_id": (C.c_int, [vp]),
+    "rs_comm_init_rank": (C.c_int, [vp, C.POINTER(vp), vp, C.c_int, C.c_int]),
+    "rs_comm_init_all": (C.c_int, [C.POINTER(vp), C.c_int, C.POINTER(vp)]),
+    "rs_comm_destroy": (C.c_int, [vp]),
+    "rs_comm_rank": (C.c_int, [vp]),
+    "rs_comm_world": (C.c_int, [vp]),
+    "rs_comm_ctx": (vp, [vp]),
+    "rs_comm_last_error": (C.c_char_p, []),
+    "rs_allgather": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_net_shard_plan": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "rs_net_layer_forward_sharded": (C.c_int, [vp, C.c_int, vp, vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "rs_net_run": (C.c_int, [vp, vp, vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "rs_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
     "rs_host_free": (C.c_int, [vp]),
     "rs_pbs_batch": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_uint32]),

@@ -15,7 +15,7 @@ SO = os.path.join(HERE, "libredsec_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CUDA_SOURCES = ["api.cu"]
-CXX_SOURCES = ["client.cpp", "layers.cpp"]
+CXX_SOURCES = ["client.cpp", "layers.cpp", "comm.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared",
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO
     extra = os.environ.get("RS_NVCC_EXTRA", "").split()      # e.g. -DRS_WAIT_HINT_NS=200u for tuning experiments
-    cmd = [NVCC] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + _sources() + ["-lgomp"]
+    cmd = [NVCC] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + _sources() + ["-lgomp", "-ldl"]
     env = dict(os.environ)
     # the image exports CC/CXX=/opt/gcc/bin/* (a wrapper without OpenMP specs); use the system g++ as nvcc's host compiler
     cmd[1:1] = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []

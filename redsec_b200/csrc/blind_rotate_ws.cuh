@@ -83,7 +83,8 @@ struct WsSmem {
     static constexpr int kBskFull = 0, kBskEmpty = STAGES, kXFull = 2 * STAGES, kXEmpty = kXFull + kCts * XSLOTS,
                          kAccReady = kXEmpty + kCts * XSLOTS, kNumBars = kAccReady + 2 * kCts;   // acc_ready[4][2]: one per accumulator polynomial
     static constexpr int kIssuedOff = kBarOff + kNumBars * 8;
-    static constexpr int kTotal = kIssuedOff + 8;
+    static constexpr int kStageSeqOff = kIssuedOff + 8;                    // int[STAGES]: last slab issued into each ring stage (row-split modes)
+    static constexpr int kTotal = kStageSeqOff + ((STAGES * 4 + 7) & ~7);
     static_assert(kCtBytes % 16 == 0, "ciphertext block must stay 16-byte aligned");
     static_assert(XSLOTS >= 3, "the inverse holds one slot; the front warp needs two more to run ahead");
 };
@@ -93,7 +94,7 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 template <int N_REGS>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N_REGS)); }
 
-template <int STAGES, int XSLOTS, int SPLIT>
+template <int STAGES, int XSLOTS, int SPLIT, bool STRESS = false>
 __global__ void __launch_bounds__(384, 1)
 blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRIDE]
                        int count, uint32_t mu,
@@ -113,6 +114,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + S::kBarOff;
     int* issued = reinterpret_cast<int*>(smem + S::kIssuedOff);
+    volatile int* stage_seq = reinterpret_cast<volatile int*>(smem + S::kStageSeqOff);
 
     // balanced partition: CTA b owns ciphertexts [b*count/grid, (b+1)*count/grid): 4 each (fewer in the last CTAs) for the
     // usual grid of ceil(count/4); at most 4/SPLIT each in the row-split modes, where the host spreads a small batch over all SMs
@@ -136,6 +138,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *issued = 0;
+        for (int s = 0; s < STAGES; s++) stage_seq[s] = -1;
     }
     __syncthreads();
 
@@ -184,8 +187,23 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                     const int prev = atomicCAS(issued, cur, cur + 1);
                     if (prev == cur) {
                         const int ns = cur % STAGES;
-                        if (cur >= STAGES)
+                        if (cur >= STAGES) {
+                            // Row-split modes: a slot's rows are SPLIT slabs apart, so a claim can run STAGES or more slabs ahead
+                            // of a lagging back-warp pair while the claim of this stage's PREVIOUS occupant (cur - STAGES) is
+                            // still parked on another front warp.  A parity wait on the empty barrier would then alias (the
+                            // barrier is two phases behind and the wanted parity equals that of an already completed phase) and
+                            // the TMA would overwrite a slab that is still being read.  Issue per stage strictly in order: wait
+                            // until the previous occupant has been ISSUED; from then on the barrier is at most one phase behind.
+                            // Un-split, a front warp never claims beyond XSLOTS + AHEAD + 1 <= STAGES slabs past its own back
+                            // warps (static_assert above), which rules the situation out, so the default path pays nothing.
+                            if (SPLIT > 1) {
+                                const long long t0 = clock64();
+                                while (stage_seq[ns] != cur - STAGES)
+                                    if (clock64() - t0 > 4000000000LL) __trap();
+                                __threadfence_block();
+                            }
                             mbar_wait_thread(bar_base + (S::kBskEmpty + ns) * 8, ((cur - STAGES) / STAGES) & 1);
+                        }
                         mbar_arrive_expect_tx(bar_base + (S::kBskFull + ns) * 8, S::kStageBytes);
                         if (l2_keep > 0.f)
                             tma_load_1d_hint(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
@@ -193,6 +211,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                         else
                             tma_load_1d(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
                                         S::kStageBytes, bar_base + (S::kBskFull + ns) * 8);
+                        if (SPLIT > 1) { __threadfence_block(); stage_seq[ns] = cur; }
                         cur++;
                     } else {
                         cur = prev;
@@ -298,6 +317,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             const int slot = rowc % XSLOTS;
             const int slab = SPLIT > 1 ? i * BK_ROWS + row * SPLIT + part : rowc;    // this slot's row r = row*SPLIT + part of step i
             const int s = slab % STAGES;
+            // stress instantiation (tests only, RS_WS_STRESS=1): one back-warp pair lags by ~a row per row, the situation the
+            // in-order slab issue above exists for
+            if (STRESS && j == 0 && (i & 3) != 3) __nanosleep(1500);
             // test the slab's barrier now and consume the answer after the transform (mbarrier round trip off the critical path)
             const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + (S::kBskFull + s) * 8, (slab / STAGES) & 1));
             // the row's exchange slot was tested before the previous row's MAC; only a miss pays the mbarrier round trip here

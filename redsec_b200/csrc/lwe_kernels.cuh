@@ -275,6 +275,13 @@ __global__ void lwe_add_const_kernel(uint32_t* __restrict__ rows, size_t count, 
         rows[c * LWE_STRIDE + LWE_N] += value;
 }
 
+// b word of row r += bias[r % mod]: the per-channel bias add of Quantize::execute / add_bias (lib/BinFunc.cpp:1063-1065,1085-1107;
+// rows are channel-fastest) as a stage of its own, for callers that compose Func objects instead of whole layers
+__global__ void lwe_add_bias_kernel(uint32_t* __restrict__ rows, size_t count, const uint32_t* __restrict__ bias, int mod) {
+    for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < count; c += (size_t)gridDim.x * blockDim.x)
+        rows[c * LWE_STRIDE + LWE_N] += bias[c % (size_t)mod];
+}
+
 // ---------------------------------------------------------------- [world][pixels][c_local] -> [pixels][world*c_local]
 __global__ void lwe_interleave_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, size_t pixels, int c_local, int world) {
     const size_t rows = pixels * (size_t)c_local * world;

@@ -65,10 +65,24 @@ class Engine:
             raise RsError(f"rs_ctx_create failed ({rc}): {self.lib.rs_last_error(None).decode()}")
         self.ctx = ctx
         self.device = device
+        self._children = []       # weak references to nets / communicators created on this context (closed before it)
+
+    def _adopt(self, child):
+        import weakref
+        self._children.append(weakref.ref(child))
 
     def close(self):
         if self.ctx:
-            self.lib.rs_ctx_destroy(self.ctx)
+            # layers, nets and communicators free their device tables through the context: close them first
+            # (rs_ctx_destroy refuses while any is alive)
+            for ref in self._children:
+                child = ref()
+                if child is not None:
+                    child.close()
+            self._children = []
+            rc = self.lib.rs_ctx_destroy(self.ctx)
+            if rc != 0:
+                raise RsError(f"rs_ctx_destroy failed ({rc}): {self.lib.rs_last_error(self.ctx).decode()}")
             self.ctx = None
 
     def _chk(self, rc: int):
@@ -102,6 +116,28 @@ class Engine:
 
     def set_stream(self, cuda_stream: int | None):
         self._chk(self.lib.rs_set_stream(self.ctx, cuda_stream))
+
+    def stream_handle(self) -> int:
+        """cudaStream_t of the selected lane (rs_get_stream), e.g. for torch.cuda.ExternalStream."""
+        h = C.c_void_p()
+        self._chk(self.lib.rs_get_stream(self.ctx, C.byref(h)))
+        return h.value or 0
+
+    def pool_trim(self):
+        self._chk(self.lib.rs_pool_trim(self.ctx))
+
+    # ---- lanes (extra streams with their own bootstrap scratch)
+    def lanes(self, n: int):
+        self._chk(self.lib.rs_lanes(self.ctx, n))
+
+    def lane_select(self, k: int):
+        self._chk(self.lib.rs_lane_select(self.ctx, k))
+
+    def lane_fork(self):
+        self._chk(self.lib.rs_lane_fork(self.ctx))
+
+    def lane_join(self):
+        self._chk(self.lib.rs_lane_join(self.ctx))
 
     # ---- hot path
     def pbs(self, inp: LweArray, mu: int, out: LweArray | None = None) -> LweArray:
@@ -222,3 +258,40 @@ class Engine:
         sm, ma, mi, sh = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
         self._chk(self.lib.rs_device_info(self.ctx, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(sh)))
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "smem_optin": sh.value}
+
+
+class Comm:
+    """NCCL communicator of one rank (rs_comm_init_rank).  `dist` is an initialised torch.distributed module: it is used once,
+    to hand rank 0's NCCL id to the other ranks; every collective afterwards is issued by the library on the engine stream."""
+
+    def __init__(self, eng: Engine, dist, rank: int, world: int):
+        import torch
+        self.eng, self.lib, self.rank, self.world = eng, eng.lib, rank, world
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            rc = self.lib.rs_comm_unique_id(ident)
+            if rc != 0:
+                raise RsError(f"rs_comm_unique_id failed ({rc}): {self.lib.rs_comm_last_error().decode()}")
+        backend = dist.get_backend()
+        dev = torch.device("cuda", eng.device) if backend == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        h = C.c_void_p()
+        rc = self.lib.rs_comm_init_rank(eng.ctx, C.byref(h), ident, rank, world)
+        if rc != 0:
+            raise RsError(f"rs_comm_init_rank failed ({rc}): {self.lib.rs_comm_last_error().decode()}")
+        self.handle = h
+        eng._adopt(self)
+
+    def allgather(self, arr: LweArray) -> LweArray:
+        out = self.eng.alloc(arr.count * self.world)
+        rc = self.lib.rs_allgather(self.handle, out.ptr, arr.ptr, arr.count)
+        if rc != 0:
+            raise RsError(f"rs_allgather failed ({rc}): {self.lib.rs_comm_last_error().decode()}")
+        return out
+
+    def close(self):
+        if self.handle:
+            self.lib.rs_comm_destroy(self.handle)
+            self.handle = None

@@ -33,7 +33,7 @@ struct tDimensions {
     uint32_t up_bound;
     float scale;
 };
-struct tConvParams { tRectangle window; bool same_pad; float tern_thresh; tRectangle stride; };
+struct tConvParams { tRectangle window; uint16_t w_max; bool same_pad; float tern_thresh; tRectangle stride; };   // lib/GPU/Layer.cuh:107-114
 struct tBNormParams { bool use_scale; float eps; };
 struct tPoolParams { tRectangle window; bool same_pad; tRectangle stride; };
 struct tQParams { uint8_t shift_bits; };
@@ -75,6 +75,14 @@ public:
     // is sharded by output pixel instead when its pixel count divides the world size: [begin,end) is then the full
     // channel range, the result holds out_count()/world rows, and the all-gather of those blocks is already canonical.
     Batch execute_shard(const Batch& in, ShardSpec shard, int* ch_begin, int* ch_end);
+    // The whole exchange step in one call, all on the context's stream (no host synchronisation): this rank's slice
+    // (execute_shard), NCCL all-gather of the slices (rs_allgather), interleave back to (h,w,c).  Consumes `in` and returns
+    // the FULL layer output on every rank -- the replicated layout of the reference's tBitPacked::enc_segs[NUM_GPUS]
+    // (lib/GPU/Layer.cuh:22-26).  comm == nullptr or world 1: same as execute().
+    Batch execute_sharded(Batch in, rs_comm* comm);
+    Batch forward_sharded(const Batch& in, rs_comm* comm);   // same without consuming `in`
+    // How the layer is split over `world` ranks: 0 = computed whole on every rank, 1 = by output-channel block, 2 = by output pixel
+    int shard_mode(int world) const;
     // uploads every device table execute()/execute_shard() needs for this rank's slice now instead of on first use
     int build_tables(ShardSpec shard = ShardSpec());
     size_t out_count() const;                             // ciphertexts in the full output
@@ -107,12 +115,61 @@ public:
     Layer* add(bool int_layer, eConvType ec, uint16_t depth, ePoolType ep, eQuantType eq, tNetParams* np);
     int prep(FILE* weights, tDimensions* input_dim);      // HeBNN::init (nets/mnist/sign1024x1/net.cpp:46-113)
     Batch run(Batch in);                                  // HeBNN::run (net.cpp:117-131); consumes in
+    Batch run_sharded(Batch in, rs_comm* comm);           // same, every layer neuron-sharded over the communicator's ranks
     size_t num_layers() const { return layers_.size(); }
     Layer* layer(size_t i) { return layers_[i].get(); }
     size_t bootstraps() const;
 private:
     rs_ctx* ctx_;
     std::vector<std::unique_ptr<Layer>> layers_;
+};
+
+// ---- Func-level stages: what {Bin,Int}Func::{Convolution,SumPooling,Quantize,MaxPooling} (lib/GPU/BinFunc_gpu.cuh:16-147,
+// lib/GPU/IntFunc_gpu.cuh) are in the reference, as batched device stages.  A caller that composes its own network from Func
+// objects (the way lib/GPU/BinLayer.cu:114-203 and IntLayer.cu:90-170 do) gets the same batched launches as redsec::Layer.
+// Every execute() consumes its input batch and returns a new one (reference ownership rule).
+class ConvStage {          // Convolution::prep / execute: ternary conv or FC on LWE rows, NO bias (Quantize adds it)
+public:
+    ConvStage(rs_ctx* ctx, bool int_inputs, uint32_t out_depth, const tConvParams& conv);
+    ~ConvStage();
+    tDimensions* prep(FILE* fd, tDimensions* dim);        // lib/BinFunc.cpp:76-133: dimension pass + ternary block
+    Batch execute(Batch in);                              // lib/BinFunc.cpp:142-330 / lib/IntFunc.cpp:152-319
+private:
+    std::unique_ptr<LayerImpl> impl_;
+};
+class SumPoolStage {       // SumPooling::prep / execute (lib/IntFunc.cpp:598-700)
+public:
+    SumPoolStage(rs_ctx* ctx, const tPoolParams& pool);
+    ~SumPoolStage();
+    tDimensions* prep(tDimensions* dim);
+    Batch execute(Batch in);
+private:
+    std::unique_ptr<LayerImpl> impl_;
+};
+class QuantizeStage {      // Quantize::prep / execute / add_bias / relu_shift (lib/BinFunc.cpp:985-1162, lib/IntFunc.cpp:800-973)
+public:
+    QuantizeStage(rs_ctx* ctx, bool int_inputs, const tQParams& q);
+    ~QuantizeStage();
+    tDimensions* prep(FILE* fd, tDimensions* dim, bool read_slope);   // bias block (+ slope block when read_slope && shift_bits > 1)
+    Batch add_bias(Batch in);                             // (0,bias[c]) + in, no bootstrap
+    // sign activation, split in two so the consumer decides the output encoding: pre_sign() adds the bias and returns the
+    // pre-activations; sign_bootstrap() is the ONE batched bootstrap, with mu = 1/4096 when a conv / the client reads the bits
+    // and mu = 1/8 when a MaxPoolStage follows (an OR gate needs +-1/8 inputs).
+    Batch pre_sign(Batch in);
+    static int sign_bootstrap(rs_ctx* ctx, Batch& pre, uint32_t mu);
+    Batch relu_shift(Batch in);                           // IntFunc only: one test-vector bootstrap per neuron
+    const std::vector<int32_t>& bias() const;
+private:
+    std::unique_ptr<LayerImpl> impl_;
+};
+class MaxPoolStage {       // MaxPooling::prep / execute (lib/BinFunc.cpp:836-925) as an OR tree
+public:
+    MaxPoolStage(rs_ctx* ctx, const tPoolParams& pool);
+    ~MaxPoolStage();
+    tDimensions* prep(tDimensions* dim);
+    Batch execute(Batch bits_eighth);                     // input bits at +-1/8, output bits at +-1/4096
+private:
+    std::unique_ptr<LayerImpl> impl_;
 };
 
 }  // namespace redsec

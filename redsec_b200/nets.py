@@ -44,6 +44,7 @@ class EncryptedNet:
         if rc != 0:
             raise RsError(f"rs_net_prep({spec['weights']}) failed with code {rc} (bad or mismatching weight file)")
         self.num_layers = self.lib.rs_net_num_layers(self.net)
+        eng._adopt(self)
 
     def build_tables(self, rank: int = 0, world: int = 1):
         """Upload every device table of this rank's slices now (otherwise built lazily by the first forward)."""
@@ -59,6 +60,22 @@ class EncryptedNet:
         self.eng._chk(self.lib.rs_net_layer_info(self.net, i, C.byref(oc), C.byref(ch), C.byref(bs), C.byref(oh), C.byref(ow)))
         return dict(out_count=oc.value, channels=ch.value, bootstraps=bs.value, out_h=oh.value, out_w=ow.value)
 
+    def shard_plan(self, i: int, world: int) -> dict:
+        """rs_net_shard_plan: mode 0 replicated / 1 channel blocks / 2 pixel blocks, rows each rank contributes, channels per block."""
+        mode, rows, cl = C.c_int(), C.c_size_t(), C.c_int()
+        self.eng._chk(self.lib.rs_net_shard_plan(self.net, i, world, C.byref(mode), C.byref(rows), C.byref(cl)))
+        return dict(mode=mode.value, rows_per_rank=rows.value, c_local=cl.value)
+
+    def run_native(self, inp: LweArray, comm=None) -> LweArray:
+        """rs_net_run: the whole network inside the library on the engine stream -- with `comm` (engine.Comm) every layer is
+        neuron-sharded and all-gathered over NCCL without a host synchronisation.  Does not consume `inp`."""
+        out, cnt = C.c_void_p(), C.c_size_t()
+        self.eng._chk(self.lib.rs_net_run(self.net, comm.handle if comm is not None else None, inp.ptr, inp.count,
+                                          C.byref(out), C.byref(cnt)))
+        arr = LweArray(self.eng, cnt.value, out.value)
+        arr._owned = True
+        return arr
+
     def bootstraps(self) -> int:
         return sum(self.layer_info(i)["bootstraps"] for i in range(self.num_layers))
 
@@ -71,17 +88,38 @@ class EncryptedNet:
         arr._owned = True     # allocated with rs_lwe_alloc inside the library; freed through rs_lwe_free
         return arr, c0.value, c1.value
 
+    def layer_forward_sharded(self, i: int, inp: LweArray, comm=None) -> LweArray:
+        """One layer, neuron-sharded over `comm` (engine.Comm; None = whole layer here): slice forward, NCCL all-gather and
+        interleave all inside the library on the engine stream.  Every rank gets the full layer output."""
+        out, cnt = C.c_void_p(), C.c_size_t()
+        self.eng._chk(self.lib.rs_net_layer_forward_sharded(self.net, i, comm.handle if comm is not None else None, inp.ptr,
+                                                            inp.count, C.byref(out), C.byref(cnt)))
+        arr = LweArray(self.eng, cnt.value, out.value)
+        arr._owned = True
+        return arr
+
+    def comm_for(self, dist):
+        """engine.Comm for dist = (torch.distributed module, rank, world), created once per engine."""
+        if dist is None or dist[2] == 1:
+            return None
+        comm = getattr(self.eng, "_comm", None)
+        if comm is None or comm.handle is None:
+            from .engine import Comm
+            comm = self.eng._comm = Comm(self.eng, *dist)
+        return comm
+
     def run(self, inp: LweArray, collect: list | None = None, dist=None, times: list | None = None) -> LweArray:
-        """HeBNN::run.  dist = (torch.distributed module, rank, world) enables neuron sharding + all-gather.
-        times: if a list, receives the host wall-clock seconds of every layer (syncs after each layer; diagnostics only)."""
+        """HeBNN::run.  dist = (torch.distributed module, rank, world) enables neuron sharding + all-gather (inside the library).
+        Without collect / times the whole network is ONE library call (rs_net_run): no host synchronisation between layers.
+        collect: receives every layer's output ciphertexts (host); times: host wall-clock seconds per layer (syncs; diagnostics)."""
         import time
+        comm = self.comm_for(dist)
+        if collect is None and times is None:
+            return self.run_native(inp, comm)
         x = inp
         for i in range(self.num_layers):
             t0 = time.perf_counter() if times is not None else 0.0
-            if dist is None or dist[2] == 1:
-                y, _, _ = self.layer_forward(i, x)
-            else:
-                y = self._layer_sharded(i, x, dist)
+            y = self.layer_forward_sharded(i, x, comm)
             if collect is not None:
                 collect.append(self.eng.download(y))
             if times is not None:
@@ -91,39 +129,6 @@ class EncryptedNet:
                 x.free()
             x = y
         return x
-
-    def _layer_sharded(self, i: int, x: LweArray, dist) -> LweArray:
-        import os
-        import time
-        import torch
-        td, rank, world = dist
-        info = self.layer_info(i)
-        dbg = os.environ.get("RS_SHARD_TIMES") and rank == 0
-        t0 = time.perf_counter()
-        y, c0, c1 = self.layer_forward(i, x, rank, world)
-        if dbg:
-            self.eng.sync(); t1 = time.perf_counter()
-        pixel_sharded = c1 - c0 == info["channels"] and y.count * world == info["out_count"]
-        if c1 - c0 == info["channels"] and not pixel_sharded:
-            return y                                   # layer not shardable: computed replicated on every rank
-        self.eng.sync()
-        dev = torch.device("cuda", self.eng.device)
-        words = y.count * LWE_STRIDE
-        local = _as_tensor(y.ptr, words, dev)
-        gathered = torch.empty(world * words, dtype=torch.int32, device=dev)
-        td.all_gather_into_tensor(gathered, local)     # NCCL over NVLink: the exchange step between layers
-        torch.cuda.current_stream(dev).synchronize()
-        if dbg:
-            print(f"  layer {i}: forward {1e3*(t1-t0):.2f} ms, all-gather of {gathered.numel()*4/1e6:.1f} MB {1e3*(time.perf_counter()-t1):.2f} ms")
-        out = self.eng.alloc(world * y.count)
-        if pixel_sharded:                              # conv-less input layer: rank blocks of pixel rows are already canonical
-            pixels, c_local, parts = world * y.count // info["channels"], info["channels"], 1
-        else:
-            pixels, c_local, parts = y.count // (c1 - c0), c1 - c0, world
-        self.eng._chk(self.lib.rs_lwe_interleave(self.eng.ctx, out.ptr, gathered.data_ptr(), pixels, c_local, parts))
-        self.eng.sync()
-        y.free()
-        return out
 
 
 def shard_range(channels: int, has_conv: bool, rank: int, world: int):

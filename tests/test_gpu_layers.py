@@ -270,3 +270,85 @@ def test_full_size_cifar_teacher_forced_signs(oracle, keyset, engine, name):
         assert ok.all(), f"{int((~ok).sum())} neurons with |pre-activation| >= {MARGIN} carry the wrong sign"
     print(f"near-threshold sign flips: observed {flips:.0f}, predicted by the 2N-rounding noise model {expected:.0f} (sigma {sigma:.2f} units)")
     assert expected < 100 or 0.8 < flips / expected < 1.25, (flips, expected)
+
+
+SAMPLE_ROWS = int(os.environ.get("RS_SAMPLE_ROWS", "1000"))
+
+
+@pytest.mark.parametrize("name", ["cifar/binarynet", "cifar/binarynet_small", "mnist/cnn_builder", "mnist/sign1024x2"])
+def test_full_size_layers_sampled_ciphertext_equality(oracle, keyset, engine, name):
+    """Full-size ciphertext parity (the oracle cannot bootstrap 636k neurons in test time, so it bootstraps a sample): run the
+    whole encrypted net on the GPU, then for EVERY layer take the GPU's own layer input and recompute, with the CPU oracle,
+    >= 1000 randomly chosen outputs of that layer -- the reference's window / pooling index formulas on the LWE rows
+    (layers_oracle.enc_linear_rows), one oracle bootstrap per neuron, and for max-pool layers the 4 sign bootstraps at 1/8 +
+    the 3 OR gates of each sampled pooled output -- and require ciphertext equality (all 351 words) with the GPU's output.
+    Row 0, the last row and the channel-tile edges are always in the sample."""
+    from oracle import layers_oracle as LO
+    nets = _nets()
+    spec = netspec.NETS[name]()
+    label, px = netspec.load_image_csv(spec["image"])
+    ct = oracle.encrypt((netspec.map_pixels(spec, px) * LO.UNIT) & 0xFFFFFFFF, 2.0 ** -15, keyset.lwe_key, 46)
+    layers = LO.prepare(spec, spec["weights"])
+    net = nets.EncryptedNet(engine, spec)
+    outs = []
+    net.run(engine.upload(ct), collect=outs)
+    net.close()
+    rng = np.random.default_rng(77)
+    x = ct
+    checked = 0
+    for li, (L, got) in enumerate(zip(layers, outs)):
+        n = got.shape[0]
+        assert n == int(np.prod(L.out_dims)), f"layer {li}: {n} rows"
+        k = min(n, SAMPLE_ROWS if not L.has_maxpool else max(SAMPLE_ROWS // 2, 1))
+        idx = np.unique(np.concatenate([rng.choice(n, size=k, replace=False), [0, n - 1, min(n - 1, 15), min(n - 1, 16)]]))
+        want = LO.enc_layer_rows(L, x, idx, keyset)
+        bad = np.nonzero((got[idx] != want).any(axis=1))[0]
+        assert bad.size == 0, f"{name} layer {li}: {bad.size} of {idx.size} sampled outputs differ from the oracle (first: row {idx[bad[0]]})"
+        checked += idx.size
+        x = got
+    print(f"{name}: {checked} sampled outputs over {len(layers)} layers ciphertext-equal to the oracle")
+
+
+def test_lanes_do_not_change_a_max_pool_layer(oracle, keyset, engine, tmp_path, monkeypatch):
+    """The block-pipelined max-pool layer (blocks of output rows issued round-robin on the context's lanes) produces the same
+    ciphertexts as the single-launch form (RS_NO_LANES=1) and as the oracle's OR tree on sampled outputs.  One conv layer of
+    CIFAR conv2's shape class: 16x16 pixels x 64 channels = 16 384 sign bootstraps -> 4 096 pooled outputs."""
+    from oracle import layers_oracle as LO
+    nets = _nets()
+    conv = dict(conv_win=(3, 3), conv_stride=(1, 1), conv_same_pad=True, e_bias=2)
+    spec = dict(name="test/pool_lanes", input=(16, 16, 8), weights=None, image=None,
+                layers=[netspec._layer("bin", "conv", 64, "max", "sign", **conv)])
+    spec["weights"] = netspec.write_random_weights(spec, str(tmp_path / "w.dat"), seed=9, p_zero=0.2, bias_range=3)
+    rng = np.random.default_rng(10)
+    bits = rng.integers(0, 2, 16 * 16 * 8) * 2 - 1
+    ct = oracle.encrypt((bits * LO.UNIT) & 0xFFFFFFFF, 2.0 ** -25, keyset.lwe_key, 47)
+    net = nets.EncryptedNet(engine, spec)
+    x = engine.upload(ct)
+    y_lanes, _, _ = net.layer_forward(0, x)
+    got = engine.download(y_lanes)
+    assert engine.lib.rs_lane_count(engine.ctx) >= 2, "the layer is large enough to be cut into blocks"
+    monkeypatch.setenv("RS_NO_LANES", "1")
+    y_single, _, _ = net.layer_forward(0, x)
+    assert np.array_equal(engine.download(y_single), got)
+    monkeypatch.delenv("RS_NO_LANES")
+    L = LO.prepare(spec, spec["weights"])[0]
+    idx = np.unique(np.concatenate([rng.choice(got.shape[0], 60, replace=False), [0, got.shape[0] - 1]]))
+    assert np.array_equal(got[idx], LO.enc_layer_rows(L, ct, idx, keyset))
+    net.close()
+
+
+def test_engine_close_order_and_error_paths_do_not_leak(keyset):
+    """rs_ctx_destroy refuses while nets are alive (their destructors free tables through the context); Engine.close
+    closes them first.  A failing forward (wrong input count) gives its temporaries back to the pool."""
+    import redsec_b200 as rs
+    nets = _nets()
+    eng = rs.Engine(0)
+    eng.load_eval_key(keyset.bsk, keyset.ksk)
+    spec = netspec.NETS["mnist/sign1024x1"]()
+    net = nets.EncryptedNet(eng, spec)
+    assert eng.lib.rs_ctx_destroy(eng.ctx) == 3 and b"still use this context" in eng.lib.rs_last_error(eng.ctx)
+    x = eng.alloc(10)                                     # wrong count for layer 0 (784)
+    with pytest.raises(rs.engine.RsError):
+        net.layer_forward(0, x)
+    eng.close()                                           # closes the net, then the context
+    assert net.net is None and eng.ctx is None

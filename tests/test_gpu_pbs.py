@@ -1,5 +1,7 @@
 """GPU parity of the bootstrap hot path against the CPU oracle, through the C-ABI.
 Bar (north star): bit-exact ciphertexts for keyswitch / sample extract / full PBS on identical inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -163,3 +165,46 @@ def test_host_entry_points_match_device(oracle, keyset, engine):
     assert np.array_equal(got, oracle.pbs(ct, MU8, keyset))
     got2 = engine.gate_host("NAND", ct, ct[::-1].copy(), MU8)
     assert np.array_equal(got2, oracle.gate("NAND", ct, ct[::-1].copy(), MU8, keyset))
+
+
+def test_2pow16_gates_truth_table_and_oracle_sample(oracle, keyset, engine):
+    """BASELINE config 2 at full size: 2^16 independent NAND and XNOR gates in one launch each; EVERY gate decrypts to the
+    truth table, and a 4 096-gate sample (a contiguous block, a strided set and the batch edges) is ciphertext-equal to
+    the CPU oracle."""
+    n = 1 << 16
+    rng = np.random.default_rng(1)
+    a_bits, b_bits = rng.integers(0, 2, n), rng.integers(0, 2, n)
+    mu8 = 1 << 29
+    a = oracle.encrypt(np.where(a_bits == 1, mu8, -mu8), 2.0 ** -25, keyset.lwe_key, 101)
+    b = oracle.encrypt(np.where(b_bits == 1, mu8, -mu8), 2.0 ** -25, keyset.lwe_key, 102)
+    d_a, d_b = engine.upload(a), engine.upload(b)
+    sample = np.unique(np.concatenate([np.arange(0, 2048), np.arange(2048, n, 31)[:2040], [n - 1, n - 2, 591, 592, 593]]))
+    for op, truth in (("NAND", 1 - (a_bits & b_bits)), ("XNOR", 1 - (a_bits ^ b_bits))):
+        got = engine.download(engine.gate(op, d_a, d_b, mu8))
+        dec = (oracle.phase(got, keyset.lwe_key).astype(np.int32) > 0).astype(np.int64)
+        assert np.array_equal(dec, truth), f"{op}: {int((dec != truth).sum())} of 2^16 gates decrypt wrong"
+        want = oracle.gate(op, a[sample], b[sample], mu8, keyset)
+        assert np.array_equal(got[sample], want), f"{op}: sampled gates differ from the oracle"
+
+
+def test_row_split_under_a_lagging_back_warp_pair(oracle, keyset):
+    """ADVICE r1 (BSK ring parity aliasing in row-split mode): the stress instantiation delays one back-warp pair of every CTA by
+    about a row per row, so front warps of the other slots run their slab claims as far ahead as the rings allow.  With the
+    in-order slab issue the ciphertexts still equal the oracle's for batch sizes that use the split kernel (<= 2 per SM)."""
+    import redsec_b200 as rs
+    os.environ["RS_WS_STRESS"] = "1"
+    try:
+        eng = rs.Engine(0)
+    finally:
+        del os.environ["RS_WS_STRESS"]
+    eng.load_eval_key(keyset.bsk, keyset.ksk)
+    rng = np.random.default_rng(12)
+    for count in (3, 150, 296):
+        mu = rng.integers(-1500, 1500, count) * (1 << 20)
+        ct = oracle.encrypt(mu, 2.0 ** -15, keyset.lwe_key, 300 + count)
+        got = eng.download(eng.pbs(eng.upload(ct), 1 << 20))
+        k = min(count, 24)
+        idx = np.unique(np.concatenate([rng.choice(count, k, replace=False), [0, count - 1]]))
+        assert np.array_equal(got[idx], oracle.pbs(ct[idx], 1 << 20, keyset)), f"count {count}"
+        # the un-stressed engine gives the same batch
+    eng.close()

@@ -99,3 +99,26 @@ def test_relu_weight_file_size_identity():
     assert [L.q_dims for L in layers] == [(14, 14, 1), (1, 1, 1024), (1, 1, 10)]
     assert layers[1].slope is not None and layers[1].slope.min() > 0 and layers[1].twin_conv and not layers[0].twin_conv
     assert netspec.map_pixels(spec, [0, 99, 100, 199, 200, 255]).tolist() == [-1, -1, 0, 0, 1, 1]
+
+
+@pytest.mark.parametrize("name", ["mnist/cnn_builder", "mnist/relu1024x1", "cifar/binarynet_small"])
+def test_sampled_linear_rows_equal_the_whole_layer(name):
+    """enc_linear_rows (what the full-size GPU parity tests sample with) against enc_linear on whole layers: integer conv with
+    the -1/4096 zero/padding convention + sum-pool (builder CNN), plaintext-twin conv (ReLU nets), binary conv with same
+    padding (CIFAR), FC after flatten, conv-less input layers.  Random uint32 rows, no bootstraps: exact mod 2^32."""
+    from oracle import layers_oracle as LO
+    from oracle import oracle as O
+    spec = netspec.NETS[name]()
+    layers = LO.prepare(spec, spec["weights"])
+    rng = np.random.default_rng(5)
+    h, w, c = spec["input"]
+    count = h * w * c
+    for li, L in enumerate(layers[:3]):
+        ct = rng.integers(0, 2 ** 32, size=(count, O.LWE_WORDS), dtype=np.uint64).astype(np.uint32)
+        n = int(np.prod(L.q_dims))
+        idx = np.unique(np.concatenate([rng.integers(0, n, 24), [0, n - 1]]))
+        if name.startswith("cifar") and li == 2:
+            break                                        # 128 x 128 x 9 x 1024 pixels as a whole layer: covered by layer 1
+        want = LO.enc_linear(L, ct)
+        assert np.array_equal(LO.enc_linear_rows(L, ct, idx), want[idx]), (name, li)
+        count = int(np.prod(L.out_dims))
