@@ -216,8 +216,8 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
 
     // ---- modswitch and accumulator init (step 2)
     const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
-    for (int i = t; i < LWE_N; i += 64) bara[i] = (uint16_t)modswitch_2N(lwe[i]);
-    const int barb = (int)modswitch_2N(lwe[LWE_N]);
+    for (int i = t; i < LWE_N; i += 64) bara[i] = (uint16_t)modswitch_2N(__ldcg(lwe + i));
+    const int barb = (int)modswitch_2N(__ldcg(lwe + LWE_N));
     const uint32_t* tv = lut ? lut + (size_t)(ct % lut_mod) * N : nullptr;
     for (int j = t; j < N; j += 64) {
         acc[j] = 0;

@@ -204,8 +204,8 @@ blind_rotate_tm_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
 
             // ---- modswitch and accumulator init (step 2)
             const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
-            for (int i = lane; i < LWE_N; i += 32) bara[i] = (uint16_t)modswitch_2N(lwe[i]);
-            const int barb = (int)modswitch_2N(lwe[LWE_N]);
+            for (int i = lane; i < LWE_N; i += 32) bara[i] = (uint16_t)modswitch_2N(__ldcg(lwe + i));
+            const int barb = (int)modswitch_2N(__ldcg(lwe + LWE_N));
             for (int k = lane; k < N; k += 32) {
                 acc[k] = 0;
                 acc[N + k] = (((k + barb) & (2 * N - 1)) < N) ? mu : 0u - mu;   // X^{2N-barb} * (mu + mu X + ...)

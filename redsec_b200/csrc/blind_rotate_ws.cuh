@@ -162,9 +162,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
 
         // ---- modswitch and accumulator init (step 2)
         const uint32_t* lwe = lwe_in + (size_t)ct * LWE_STRIDE;
-        for (int i = lane; i < LWE_N; i += 32) bara[i] = (uint16_t)modswitch_2N(lwe[i]);
+        for (int i = lane; i < LWE_N; i += 32) bara[i] = (uint16_t)modswitch_2N(__ldcg(lwe + i));
         if (part == 0) {
-            const int barb = (int)modswitch_2N(lwe[LWE_N]);
+            const int barb = (int)modswitch_2N(__ldcg(lwe + LWE_N));
             const uint32_t* tv = lut ? lut + (size_t)(ct % lut_mod) * N : nullptr;
             for (int k = lane; k < N; k += 32) {
                 acc[k] = 0;

@@ -809,15 +809,18 @@ ConvStage::ConvStage(rs_ctx* ctx, bool int_inputs, uint32_t out_depth, const tCo
     impl_->int_inputs = int_inputs; impl_->ec = E_CONV; impl_->depth = (uint16_t)out_depth;
 }
 ConvStage::~ConvStage() = default;
+int ConvStage::out_depth() const { return impl_->cout_dep; }
 tDimensions* ConvStage::prep(FILE* fd, tDimensions* dim) {
     if (impl_->prep_conv(fd, dim) != RS_OK) { printf("Bad Weights File. Exiting...\r\n"); return nullptr; }
     impl_->prepared = true;
     return dim;
 }
-Batch ConvStage::execute(Batch in) {
+Batch ConvStage::execute(Batch in, int c0, int c1) {
     Rows out(impl_->ctx);
     size_t n = 0;
-    const int rc = impl_->prepared ? impl_->run_conv(in.dev, in.count, 0, impl_->cout_dep, false, &out, &n) : RS_ERR_STATE;
+    if (c1 < 0) c1 = impl_->cout_dep;
+    int rc = (impl_->prepared && c0 >= 0 && c0 < c1 && c1 <= impl_->cout_dep) ? RS_OK : RS_ERR_STATE;
+    if (rc == RS_OK) rc = impl_->run_conv(in.dev, in.count, c0, c1, false, &out, &n);
     return consume(impl_->ctx, in, rc, out, n);
 }
 
@@ -837,8 +840,10 @@ Batch SumPoolStage::execute(Batch in) {
     Rows out(impl_->ctx);
     DevCsr* sp = nullptr;
     int rc = impl_->prepared ? RS_OK : RS_ERR_STATE;
-    if (rc == RS_OK && in.count != (size_t)impl_->sp_in_h * impl_->sp_in_w * impl_->q_dep) rc = RS_ERR_ARG;
-    if (rc == RS_OK) rc = impl_->sumpool_table(0, impl_->q_dep, false, &sp);
+    const size_t pixels = (size_t)impl_->sp_in_h * impl_->sp_in_w;
+    const int cl = pixels ? (int)(in.count / pixels) : 0;           // a channel slice pools like the full layer
+    if (rc == RS_OK && (cl < 1 || cl > impl_->q_dep || (size_t)cl * pixels != in.count)) rc = RS_ERR_ARG;
+    if (rc == RS_OK) rc = impl_->sumpool_table(0, cl, false, &sp);
     if (rc == RS_OK) rc = out.alloc(sp->rows);
     if (rc == RS_OK) rc = sp->apply(out.p, in.dev);
     return consume(impl_->ctx, in, rc, out, sp ? sp->rows : 0);
@@ -851,6 +856,7 @@ QuantizeStage::QuantizeStage(rs_ctx* ctx, bool int_inputs, const tQParams& q) : 
 }
 QuantizeStage::~QuantizeStage() = default;
 const std::vector<int32_t>& QuantizeStage::bias() const { return impl_->bias_int; }
+int QuantizeStage::channels() const { return impl_->q_dep; }
 tDimensions* QuantizeStage::prep(FILE* fd, tDimensions* dim, bool read_slope) {
     if (impl_->prep_quant(fd, dim, read_slope && impl_->np.quant.shift_bits > 1) != RS_OK) { printf("Bad Weights File. Exiting...\r\n"); return nullptr; }
     if (impl_->ctx) {
@@ -860,25 +866,29 @@ tDimensions* QuantizeStage::prep(FILE* fd, tDimensions* dim, bool read_slope) {
     impl_->prepared = true;
     return dim;
 }
-Batch QuantizeStage::add_bias(Batch in) {
+Batch QuantizeStage::add_bias(Batch in, int c0) {
     Batch fail;
-    if (!impl_->prepared || !impl_->ctx || in.count != (size_t)impl_->q_h * impl_->q_w * impl_->q_dep ||
-        rs_lwe_add_bias(impl_->ctx, in.dev, in.count, (const uint32_t*)impl_->bias_dev, impl_->q_dep) != RS_OK) {
+    const size_t pixels = (size_t)impl_->q_h * impl_->q_w;
+    const int cl = pixels ? (int)(in.count / pixels) : 0;
+    if (!impl_->prepared || !impl_->ctx || cl < 1 || c0 < 0 || c0 + cl > impl_->q_dep || (size_t)cl * pixels != in.count ||
+        rs_lwe_add_bias(impl_->ctx, in.dev, in.count, (const uint32_t*)impl_->bias_dev + c0, cl) != RS_OK) {
         if (impl_->ctx) rs_lwe_free(impl_->ctx, in.dev);
         return fail;
     }
     return in;      // in place: the "fresh array" of the reference is the same rows
 }
-Batch QuantizeStage::pre_sign(Batch in) { return add_bias(in); }
+Batch QuantizeStage::pre_sign(Batch in, int c0) { return add_bias(in, c0); }
 int QuantizeStage::sign_bootstrap(rs_ctx* ctx, Batch& pre, uint32_t mu) {
     return rs_pbs_batch(ctx, pre.dev, pre.dev, pre.count, mu);
 }
-Batch QuantizeStage::relu_shift(Batch in) {
+Batch QuantizeStage::relu_shift(Batch in, int c0) {
     Batch fail;
     void* lut = nullptr;
-    int rc = (impl_->prepared && impl_->is_relu() && in.count == (size_t)impl_->q_h * impl_->q_w * impl_->q_dep) ? RS_OK : RS_ERR_STATE;
-    if (rc == RS_OK) rc = impl_->relu_tables(0, impl_->q_dep, &lut);
-    if (rc == RS_OK) rc = rs_pbs_lut_batch(impl_->ctx, in.dev, in.dev, in.count, (const uint32_t*)lut, impl_->q_dep);
+    const size_t pixels = (size_t)impl_->q_h * impl_->q_w;
+    const int cl = pixels ? (int)(in.count / pixels) : 0;
+    int rc = (impl_->prepared && impl_->is_relu() && cl >= 1 && c0 >= 0 && c0 + cl <= impl_->q_dep && (size_t)cl * pixels == in.count) ? RS_OK : RS_ERR_STATE;
+    if (rc == RS_OK) rc = impl_->relu_tables(c0, c0 + cl, &lut);
+    if (rc == RS_OK) rc = rs_pbs_lut_batch(impl_->ctx, in.dev, in.dev, in.count, (const uint32_t*)lut, cl);
     if (rc == RS_OK) rc = rs_lwe_add_const(impl_->ctx, in.dev, in.count, impl_->relu_half());
     if (rc != RS_OK) { if (impl_->ctx) rs_lwe_free(impl_->ctx, in.dev); return fail; }
     return in;
@@ -895,27 +905,31 @@ tDimensions* MaxPoolStage::prep(tDimensions* dim) {
     impl_->prepared = true;
     return dim;
 }
-// Same OR tree as the layer forward, fed with bits that are already bootstrapped at +-1/8: the tree buffer's first in_count
-// rows are the input itself.
-Batch MaxPoolStage::execute(Batch bits) {
+Batch MaxPoolStage::execute_from_preact(Batch pre) {
     rs_ctx* ctx = impl_->ctx;
-    Rows pooled(ctx), tree(ctx), scratch(ctx);
-    PoolPlan* plan = nullptr;
-    int rc = impl_->prepared && ctx ? RS_OK : RS_ERR_STATE;
-    if (rc == RS_OK) rc = impl_->maxpool_plan(impl_->q_dep, &plan);
-    if (rc == RS_OK && plan->in_count != bits.count) rc = RS_ERR_ARG;
-    if (rc == RS_OK) rc = tree.alloc(plan->buf_count);
-    if (rc == RS_OK) rc = scratch.alloc(bits.count);
-    if (rc == RS_OK) rc = pooled.alloc(plan->out_count);
-    if (rc == RS_OK) rc = rs_lwe_copy(ctx, tree.p, bits.dev, bits.count);   // the input bits are the head of the tree buffer
-    if (rc == RS_OK)
-        for (auto& st : plan->steps) {
-            rc = st->csr.apply(scratch.p, tree.p);
-            if (rc == RS_OK) rc = rs_pbs_batch(ctx, tree.p + st->dst_offset * RS_LWE_STRIDE, scratch.p, st->csr.rows, st->mu);
-            if (rc != RS_OK) break;
-        }
-    if (rc == RS_OK) rc = plan->final_gather.apply(pooled.p, tree.p);
-    return consume(ctx, bits, rc, pooled, plan ? plan->out_count : 0);
+    Rows pooled(ctx);
+    size_t n = 0;
+    const size_t pixels = (size_t)impl_->q_h * impl_->q_w;
+    const int cl = pixels ? (int)(pre.count / pixels) : 0;
+    int rc = (impl_->prepared && ctx && cl >= 1 && cl <= impl_->q_dep && (size_t)cl * pixels == pre.count) ? RS_OK : RS_ERR_STATE;
+    if (rc == RS_OK) rc = impl_->run_maxpool_sign(pre.dev, pre.count, cl, &pooled, &n);
+    return consume(ctx, pre, rc, pooled, n);
+}
+
+Batch gather_channels(rs_ctx* ctx, rs_comm* comm, Batch part, int c_local) {
+    Batch fail;
+    const int world = rs_comm_world(comm);
+    if (!comm || world <= 1) return part;
+    Rows mine(ctx), gathered(ctx), full(ctx);
+    mine.reset(part.dev);
+    if (c_local < 1 || part.count % (size_t)c_local) return fail;
+    if (gathered.alloc(part.count * world) != RS_OK) return fail;
+    if (rs_allgather(comm, gathered.p, mine.p, part.count) != RS_OK) return fail;
+    if (full.alloc(part.count * world) != RS_OK) return fail;
+    if (rs_lwe_interleave(ctx, full.p, gathered.p, part.count / c_local, c_local, world) != RS_OK) return fail;
+    Batch out;
+    out.dev = full.release(); out.count = part.count * world;
+    return out;
 }
 
 }  // namespace redsec

@@ -1,5 +1,10 @@
 // redsec_b200/csrc/lwe_kernels.cuh -- integer LWE kernels: keyswitch, gate pre-combination, ternary linear layers.
 // All arithmetic is uint32 wrap-around (torus32), so results are bit-exact by construction.
+// Loads of data that an EARLIER KERNEL wrote (ciphertext rows, extracted samples) use __ldcg (ld.global.cg: cached in L2 only).
+// The compiler turns plain loads through const __restrict__ pointers into LDG.E.CONSTANT (the non-coherent L1 path), which is
+// only coherent at kernel boundaries of an otherwise idle SM: with several lanes in flight (rs_lanes) an SM runs CTAs of other
+// kernels back to back without its L1 being invalidated, and a buffer that is rewritten between two launches (the gate
+// pre-combination scratch, the extracted-sample scratch) was then read stale by a later launch landing on the same SM.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -44,7 +49,7 @@ __global__ void keyswitch_init_kernel(const uint32_t* __restrict__ ext, int coun
     for (; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t c = idx / LWE_STRIDE;
         const int x = (int)(idx % LWE_STRIDE);
-        lwe_out[idx] = (x == LWE_N) ? ext[c * EXT_STRIDE + N] : 0u;
+        lwe_out[idx] = (x == LWE_N) ? __ldcg(ext + c * EXT_STRIDE + N) : 0u;
     }
 }
 
@@ -78,7 +83,7 @@ keyswitch_tiled_kernel(const uint32_t* __restrict__ ext,      // [count][EXT_STR
     // a'_i + prec_offset for the tile, transposed to [i][ciphertext] (coalesced reads of ir consecutive words per row)
     for (int idx = threadIdx.x; idx < ir * TILE; idx += blockDim.x) {
         const int c = idx / ir, il = idx % ir;
-        abar[il * TILE + c] = (c < tile) ? ext[(size_t)(first + c) * EXT_STRIDE + i0 + il] + KS_PREC_OFFSET : 0u;   // 0 => all digits 0
+        abar[il * TILE + c] = (c < tile) ? __ldcg(ext + (size_t)(first + c) * EXT_STRIDE + i0 + il) + KS_PREC_OFFSET : 0u;   // 0 => all digits 0
     }
     __syncthreads();
 
@@ -167,7 +172,7 @@ keyswitch_kernel(const uint32_t* __restrict__ ext,      // [count][EXT_STRIDE]
     const int first = blockIdx.x * KS_TILE;
     const int tile = min(KS_TILE, count - first);
     for (int c = 0; c < tile; c++)
-        for (int i = x; i < N; i += LWE_STRIDE) abar[c][i] = ext[(size_t)(first + c) * EXT_STRIDE + i] + KS_PREC_OFFSET;
+        for (int i = x; i < N; i += LWE_STRIDE) abar[c][i] = __ldcg(ext + (size_t)(first + c) * EXT_STRIDE + i) + KS_PREC_OFFSET;
     __syncthreads();
     uint32_t acc[KS_TILE];
 #pragma unroll
@@ -191,7 +196,7 @@ keyswitch_kernel(const uint32_t* __restrict__ ext,      // [count][EXT_STRIDE]
     for (int c = 0; c < KS_TILE; c++) {
         if (c < tile) {
             uint32_t v = acc[c];
-            if (x == LWE_N) v += ext[(size_t)(first + c) * EXT_STRIDE + N];
+            if (x == LWE_N) v += __ldcg(ext + (size_t)(first + c) * EXT_STRIDE + N);
             if (x > LWE_N) v = 0;
             lwe_out[(size_t)(first + c) * LWE_STRIDE + x] = v;
         }
@@ -206,7 +211,7 @@ __global__ void ksk_pad_kernel(const uint32_t* __restrict__ src /*[rows][351]*/,
     for (; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         size_t r = idx / LWE_STRIDE;
         int x = (int)(idx % LWE_STRIDE);
-        dst[idx] = x < LWE_WORDS ? src[r * LWE_WORDS + x] : 0u;
+        dst[idx] = x < LWE_WORDS ? __ldcg(src + r * LWE_WORDS + x) : 0u;
     }
 }
 
@@ -217,7 +222,7 @@ __global__ void lwe_pad_kernel(const uint32_t* __restrict__ src, uint32_t* __res
     for (; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         size_t r = idx / LWE_STRIDE;
         int x = (int)(idx % LWE_STRIDE);
-        dst[idx] = x < LWE_WORDS ? src[r * LWE_WORDS + x] : 0u;
+        dst[idx] = x < LWE_WORDS ? __ldcg(src + r * LWE_WORDS + x) : 0u;
     }
 }
 __global__ void lwe_unpad_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int count) {
@@ -226,7 +231,7 @@ __global__ void lwe_unpad_kernel(const uint32_t* __restrict__ src, uint32_t* __r
     for (; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         size_t r = idx / LWE_WORDS;
         int x = (int)(idx % LWE_WORDS);
-        dst[idx] = src[r * LWE_STRIDE + x];
+        dst[idx] = __ldcg(src + r * LWE_STRIDE + x);
     }
 }
 
@@ -238,7 +243,7 @@ __global__ void gate_linear_kernel(uint32_t* __restrict__ out, const uint32_t* _
     size_t total = (size_t)count * LWE_STRIDE;
     for (; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int x = (int)(idx % LWE_STRIDE);
-        uint32_t v = m * (in0[idx] + in1[idx]);
+        uint32_t v = m * (__ldcg(in0 + idx) + __ldcg(in1 + idx));
         if (x == LWE_N) v += fix;
         if (x > LWE_N) v = 0;
         out[idx] = v;
@@ -260,7 +265,7 @@ lwe_lincomb_kernel(uint32_t* __restrict__ out, int out_count, const uint32_t* __
         uint4 acc = make_uint4(0, 0, 0, 0);
         const int k0 = rowptr[o], k1 = rowptr[o + 1];
         for (int k = k0; k < k1; k++) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (size_t)col[k] * LWE_STRIDE) + x);
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(in + (size_t)col[k] * LWE_STRIDE) + x);
             const uint32_t s = (uint32_t)(int32_t)sign[k];
             acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w;
         }
@@ -290,7 +295,7 @@ __global__ void lwe_interleave_kernel(uint4* __restrict__ out, const uint4* __re
         const size_t pix = row / ((size_t)c_local * world);
         const int ch = (int)(row % ((size_t)c_local * world));
         const int r = ch / c_local, c = ch % c_local;
-        out[row * (LWE_STRIDE / 4) + x] = in[(((size_t)r * pixels + pix) * c_local + c) * (LWE_STRIDE / 4) + x];
+        out[row * (LWE_STRIDE / 4) + x] = __ldcg(in + (((size_t)r * pixels + pix) * c_local + c) * (LWE_STRIDE / 4) + x);
     }
 }
 
@@ -339,7 +344,7 @@ lwe_conv_kernel(uint32_t* __restrict__ out,             // [out_h*out_w][od_end-
             const int8_t* wk = wt + (size_t)((fh * d.win_w + fw) * d.in_dep) * CONV_OD_TILE;
 #pragma unroll 2
             for (int di = 0; di < d.in_dep; di++) {
-                const uint4 v = __ldg(src + (size_t)di * (LWE_STRIDE / 4));
+                const uint4 v = __ldcg(src + (size_t)di * (LWE_STRIDE / 4));
                 const uint4 wq = __ldg(reinterpret_cast<const uint4*>(wk + (size_t)di * CONV_OD_TILE));
                 const uint32_t wwords[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll

@@ -295,3 +295,10 @@ class Comm:
         if self.handle:
             self.lib.rs_comm_destroy(self.handle)
             self.handle = None
+
+    def __del__(self):
+        try:
+            if self.eng.ctx:
+                self.close()
+        except Exception:
+            pass

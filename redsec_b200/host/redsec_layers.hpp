@@ -128,12 +128,16 @@ private:
 // lib/GPU/IntFunc_gpu.cuh) are in the reference, as batched device stages.  A caller that composes its own network from Func
 // objects (the way lib/GPU/BinLayer.cu:114-203 and IntLayer.cu:90-170 do) gets the same batched launches as redsec::Layer.
 // Every execute() consumes its input batch and returns a new one (reference ownership rule).
+// Channel slices: with several GPUs a caller computes output channels [c0,c1) of a conv on each device, runs the pooling /
+// quantize / max-pool stages on the slice (they are per channel) and restores the full layer with gather_channels() before
+// the next conv.  c1 < 0 means "all channels".
 class ConvStage {          // Convolution::prep / execute: ternary conv or FC on LWE rows, NO bias (Quantize adds it)
 public:
     ConvStage(rs_ctx* ctx, bool int_inputs, uint32_t out_depth, const tConvParams& conv);
     ~ConvStage();
     tDimensions* prep(FILE* fd, tDimensions* dim);        // lib/BinFunc.cpp:76-133: dimension pass + ternary block
-    Batch execute(Batch in);                              // lib/BinFunc.cpp:142-330 / lib/IntFunc.cpp:152-319
+    Batch execute(Batch in, int c0 = 0, int c1 = -1);     // lib/BinFunc.cpp:142-330 / lib/IntFunc.cpp:152-319; rows (oh,ow,c0..c1)
+    int out_depth() const;
 private:
     std::unique_ptr<LayerImpl> impl_;
 };
@@ -142,7 +146,7 @@ public:
     SumPoolStage(rs_ctx* ctx, const tPoolParams& pool);
     ~SumPoolStage();
     tDimensions* prep(tDimensions* dim);
-    Batch execute(Batch in);
+    Batch execute(Batch in);                              // channel count inferred from in.count (full layer or a slice)
 private:
     std::unique_ptr<LayerImpl> impl_;
 };
@@ -151,14 +155,15 @@ public:
     QuantizeStage(rs_ctx* ctx, bool int_inputs, const tQParams& q);
     ~QuantizeStage();
     tDimensions* prep(FILE* fd, tDimensions* dim, bool read_slope);   // bias block (+ slope block when read_slope && shift_bits > 1)
-    Batch add_bias(Batch in);                             // (0,bias[c]) + in, no bootstrap
+    Batch add_bias(Batch in, int c0 = 0);                 // (0,bias[c0+c]) + in, no bootstrap; in place
     // sign activation, split in two so the consumer decides the output encoding: pre_sign() adds the bias and returns the
     // pre-activations; sign_bootstrap() is the ONE batched bootstrap, with mu = 1/4096 when a conv / the client reads the bits
     // and mu = 1/8 when a MaxPoolStage follows (an OR gate needs +-1/8 inputs).
-    Batch pre_sign(Batch in);
+    Batch pre_sign(Batch in, int c0 = 0);
     static int sign_bootstrap(rs_ctx* ctx, Batch& pre, uint32_t mu);
-    Batch relu_shift(Batch in);                           // IntFunc only: one test-vector bootstrap per neuron
+    Batch relu_shift(Batch in, int c0 = 0);               // IntFunc only: one test-vector bootstrap per neuron
     const std::vector<int32_t>& bias() const;
+    int channels() const;
 private:
     std::unique_ptr<LayerImpl> impl_;
 };
@@ -167,9 +172,13 @@ public:
     MaxPoolStage(rs_ctx* ctx, const tPoolParams& pool);
     ~MaxPoolStage();
     tDimensions* prep(tDimensions* dim);
-    Batch execute(Batch bits_eighth);                     // input bits at +-1/8, output bits at +-1/4096
+    // `pre` holds the PRE-activations of the sign stage (QuantizeStage::pre_sign); this stage issues the sign bootstrap at 1/8,
+    // the OR tree, and emits bits at +-1/4096 -- the same block-pipelined launches as redsec::Layer
+    Batch execute_from_preact(Batch pre);
 private:
     std::unique_ptr<LayerImpl> impl_;
 };
+// restores the full (h,w,C) layer from every rank's channel slice [pixel][c_local]: all-gather + interleave; consumes `part`
+Batch gather_channels(rs_ctx* ctx, rs_comm* comm, Batch part, int c_local);
 
 }  // namespace redsec

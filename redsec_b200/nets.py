@@ -55,6 +55,13 @@ class EncryptedNet:
             self.lib.rs_net_destroy(self.net)
             self.net = None
 
+    def __del__(self):      # a net dropped without close() must still give its context reference back
+        try:
+            if self.eng.ctx:
+                self.close()
+        except Exception:
+            pass
+
     def layer_info(self, i: int) -> dict:
         oc, ch, bs, oh, ow = C.c_size_t(), C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
         self.eng._chk(self.lib.rs_net_layer_info(self.net, i, C.byref(oc), C.byref(ch), C.byref(bs), C.byref(oh), C.byref(ow)))
