@@ -31,6 +31,25 @@ struct PubKey {
     ~PubKey();
 };
 
+typedef uint32_t Torus;                                   // torus32, as (RED)cuFHE's
+inline Torus ModSwitchToTorus(int32_t mu, int32_t space) { return rs_modswitch_to_torus32(mu, space); }   // lib/GPU/gates.cu:125
+
+// (RED)cuFHE's per-ciphertext launches take a Stream (lib/GPU/gates.cuh).  The engine batches and orders its own work, so the
+// facade's Stream only has to exist and be creatable / destroyable the way lib/GPU/BinFunc_gpu.cu:116-138 does it.
+class Stream {
+public:
+    Stream() = default;
+    Stream(int) {}                                        // the reference passes a plain int in places
+    void Create() {}
+    void Destroy() {}
+    cudaStream_t st() const { return nullptr; }
+};
+
+void Copy(Ctxt& out, const Ctxt& in, Stream st = Stream());        // host copy of one sample
+inline void Copy(Ctxt& out, const Ctxt* in, Stream st = Stream()) { Copy(out, *in, st); }   // lib/GPU/BinOps_gpu.cu:124 passes a pointer
+void Not(Ctxt& out, const Ctxt& in, Stream st = Stream());         // LWE negation (NotOp, lib/GPU/gates.cu:110-122)
+inline void Not(Ctxt& out, const Ctxt* in, Stream st = Stream()) { Not(out, *in, st); }
+
 void ReadPubKeyFromFile(PubKey& key, const char* path);   // nets/*/net.cu:43
 void Initialize(PubKey& key);                             // once per device, after cudaSetDevice (net.cu:45-48)
 void ReadCtxtFromFileRed(Ctxt& ct, std::ifstream& in);    // main.cu:67: next record of image.ctxt
@@ -39,5 +58,8 @@ void Synchronize();                                       // main.cu:74
 void CuCheckError();                                      // main.cu:75: aborts with the engine's last error, as the macro did
 void CleanUp();                                           // main.cu:84
 rs_ctx* CurrentContext();                                 // the engine context of the calling thread's current device (shim-internal)
+rs_ctx* ContextOf(int device);                            // ... of a given device (NULL if Initialize was not called on it)
+// communicator of `device` in the single-process group over devices 0..n-1 (created on first use; NULL when n == 1)
+rs_comm* CommunicatorOf(int device, int n);
 
 }  // namespace redcufhe

@@ -12,6 +12,6 @@ public:
     void set_print_layer(uint8_t i);
     tDimensions in_dim, out_dim;
 private:
-    redsec::Layer* impl_;
+    redsec::Layer* impl_[NUM_GPUS];
     eQuantType quant_;
 };

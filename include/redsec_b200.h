@@ -147,6 +147,10 @@ int rs_lwe_conv(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *in_dev, const in
                 const uint32_t *bias_dev /* [out_dep] torus32, may be NULL */, const rs_conv_desc *desc);
 /* dev[c].b += value for every row (adds the trivial sample (0,value)); lweNoiselessTrivial + lweAddTo, lib/BinOps_enc.cpp:137-141 */
 int rs_lwe_add_const(rs_ctx *ctx, uint32_t *dev, size_t count, uint32_t value);
+/* out = (0,fix) + m0*in0 + m1*in1 (in1 may be NULL; in place allowed): add_int / sub_int / mul_int / levelNOT of
+ * lib/GPU/gates.cu:110-122,158-212 (AddOp / SubOp / NotOp) and lweAddTo / lweSubTo / lweAddMulTo for a batch */
+int rs_lwe_axpby(rs_ctx *ctx, uint32_t *out_dev, const uint32_t *in0_dev, const uint32_t *in1_dev, size_t count, uint32_t m0,
+                 uint32_t m1, uint32_t fix);
 /* dev[r].b += bias_dev[r % mod] (per-channel bias, rows channel-fastest): the bias add of {Bin,Int}Func::Quantize::execute /
  * add_bias (lib/BinFunc.cpp:1063-1065,1085-1107) as a stage of its own for callers that compose Func objects */
 int rs_lwe_add_bias(rs_ctx *ctx, uint32_t *dev, size_t count, const uint32_t *bias_dev, int mod);

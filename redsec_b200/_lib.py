@@ -33,6 +33,7 @@ SIGNATURES = {
     "rs_lwe_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "rs_lwe_download": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "rs_lwe_copy": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rs_lwe_axpby": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32]),
     "rs_lwe_add_bias": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_int]),
     "rs_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
     "rs_ctx_device": (C.c_int, [vp]),

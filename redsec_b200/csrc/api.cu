@@ -753,6 +753,19 @@ int rs_lwe_add_bias(rs_ctx* ctx, uint32_t* dev, size_t count, const uint32_t* bi
     return RS_OK;
 }
 
+int rs_lwe_axpby(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* in0_dev, const uint32_t* in1_dev, size_t count, uint32_t m0,
+                 uint32_t m1, uint32_t fix) {
+    DeviceGuard dg(ctx);
+    if (!ctx || !out_dev || !in0_dev) return fail(ctx, RS_ERR_ARG, "rs_lwe_axpby: NULL argument");
+    if (count == 0) return RS_OK;
+    {
+        LaunchScope ls(ctx, RS_K_LINEAR);
+        rs::lwe_axpby_kernel<<<grid_for(ctx, count * rs::LWE_STRIDE, 256), 256, 0, ctx->stream>>>(out_dev, in0_dev, in1_dev, count, m0, m1, fix);
+    }
+    RS_CUDA(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
 int rs_ctx_device(const rs_ctx* ctx) { return ctx ? ctx->device : -1; }
 int rs_get_stream(rs_ctx* ctx, void** cuda_stream) {
     if (!ctx || !cuda_stream) return RS_ERR_ARG;

@@ -250,6 +250,20 @@ __global__ void gate_linear_kernel(uint32_t* __restrict__ out, const uint32_t* _
     }
 }
 
+// out = (0, fix) + m0 * in0 + m1 * in1: add_int / sub_int / mul_int / levelNOT of lib/GPU/gates.cu:110-122,158-202 for a batch
+__global__ void lwe_axpby_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ in0, const uint32_t* __restrict__ in1,
+                                 size_t count, uint32_t m0, uint32_t m1, uint32_t fix) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = count * LWE_STRIDE;
+    for (; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % LWE_STRIDE);
+        uint32_t v = m0 * __ldcg(in0 + idx) + (in1 ? m1 * __ldcg(in1 + idx) : 0u);
+        if (x == LWE_N) v += fix;
+        if (x > LWE_N) v = 0;
+        out[idx] = v;
+    }
+}
+
 // ---------------------------------------------------------------- ternary linear layer on LWE rows (a10 / f1)
 // out[o] = (0, bias[o]) + sum_{k in [rowptr[o], rowptr[o+1])} sign[k] * in[col[k]]
 // Covers BinFunc/IntFunc Convolution::execute, SumPooling::execute, Quantize bias add, add_bias

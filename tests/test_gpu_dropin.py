@@ -1,6 +1,11 @@
-"""Drop-in check (SURVEY 8b "B-outer", row f3): the reference's own, UNMODIFIED GPU drivers (nets/*/main.cu + net.cu, built by
-dropin/build.sh with the reference Makefile's command lines against this repo's REDcuFHE facade) run on the GPU box and must
-write the same output ciphertexts as the engine's own EncryptedNet on the same keyset and image ciphertexts."""
+"""Drop-in check (SURVEY 8b "B-outer", rows f3 / b-ops): the reference's own, UNMODIFIED GPU drivers (nets/*/main.cu + net.cu,
+built by dropin/build.sh with the reference Makefile's command lines against this repo's REDcuFHE facade) run on the GPU box
+and must write the same output ciphertexts as the engine's own EncryptedNet on the same keyset and image ciphertexts.
+
+Trees: `tree` = Layer-level facade (this repo's IntLayer / BinLayer); `tree_func` = the REFERENCE's own
+lib/GPU/{Bin,Int}Layer.cu, unmodified, sequencing this repo's BinFunc:: / IntFunc:: classes (a network composed from Func
+objects); `*_g<N>` = the same built with NUM_GPUS = N: one process, one host thread and one engine context per GPU, layers
+neuron-sharded with an NCCL all-gather between them -- the output must equal the single-GPU ciphertexts bit for bit."""
 import os
 import subprocess
 
@@ -11,16 +16,28 @@ from redsec_b200 import netspec
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TREE = os.path.join(ROOT, "dropin", "_build", "tree")
+BUILD = os.path.join(ROOT, "dropin", "_build")
+
+CASES = [("tree", "mnist/sign1024x1", 1), ("tree", "mnist/sign1024x3", 1), ("tree", "cifar/binarynet_small", 1),
+         ("tree_func", "mnist/sign1024x1", 1), ("tree_func", "cifar/binarynet_small", 1),
+         ("tree_g2", "mnist/sign1024x1", 2), ("tree_g2", "cifar/binarynet_small", 2), ("tree_func_g2", "cifar/binarynet_small", 2),
+         ("tree_g8", "cifar/binarynet", 8)]
 
 
-@pytest.mark.parametrize("name", ["mnist/sign1024x1", "mnist/sign1024x3", "cifar/binarynet_small"])
-def test_reference_gpu_driver_runs_on_the_engine(engine, keyset, name):
+def _gpu_count() -> int:
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("tree,name,ngpu", CASES, ids=[f"{t}-{n}" for t, n, _ in CASES])
+def test_reference_gpu_driver_runs_on_the_engine(engine, keyset, tree, name, ngpu):
     from redsec_b200 import client, nets
-    exe = os.path.join(TREE, "nets", name, "gpu-encrypt.out")
+    exe = os.path.join(BUILD, tree, "nets", name, "gpu-encrypt.out")
     if not os.path.exists(exe):
         pytest.skip("dropin/_build is not built (needs the reference tree at build time: dropin/build.sh)")
-    cdir = os.path.join(TREE, "client")
+    if _gpu_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs on the box, {_gpu_count()} present")
+    cdir = os.path.join(BUILD, tree, "client")
     os.makedirs(cdir, exist_ok=True)
     ks = client.KeySet(keyset.lwe_key, keyset.tlwe_key, keyset.bsk, keyset.ksk)
     eval_key = os.path.join(cdir, "eval.key")
@@ -34,9 +51,9 @@ def test_reference_gpu_driver_runs_on_the_engine(engine, keyset, name):
     if os.path.exists(out_path):
         os.remove(out_path)                      # the driver appends (main.cu:82)
     env = dict(os.environ)
-    env["LD_LIBRARY_PATH"] = os.pathsep.join([os.path.join(ROOT, "dropin", "_build", "lib"), os.path.join(ROOT, "redsec_b200"),
+    env["LD_LIBRARY_PATH"] = os.pathsep.join([os.path.join(BUILD, "lib"), os.path.join(ROOT, "redsec_b200"),
                                               env.get("LD_LIBRARY_PATH", "")])
-    r = subprocess.run([exe], cwd=os.path.dirname(exe), env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe], cwd=os.path.dirname(exe), env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "Inference Time" in r.stdout
     got = client.read_ctxt(out_path, 10)
@@ -45,6 +62,6 @@ def test_reference_gpu_driver_runs_on_the_engine(engine, keyset, name):
     net.close()
     assert np.array_equal(got, want), "reference driver over the facade and EncryptedNet disagree"
     scores = client.decrypt(got, ks.lwe_key, 4096)
-    print(name, "scores", scores.tolist(), "label", label, r.stdout.strip().splitlines()[-1])
+    print(tree, name, "scores", scores.tolist(), "label", label, r.stdout.strip().splitlines()[-1])
     if name.startswith("mnist"):
         assert int(np.argmax(scores)) == label
