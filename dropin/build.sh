@@ -71,10 +71,22 @@ build_tree() {
   return 0
 }
 
+# a caller of the Ops-level surface (gates.cuh / BinOps:: / IntOps::), linked like a net driver
+build_ops_check() {
+  local T=$B/$1
+  mkdir -p "$T/opscheck"
+  ( cd "$T/opscheck"
+    $NVCC $CCBIN -O2 -std=c++17 -x cu -c -o ops_check.o "$ROOT/dropin/src/ops_check.cpp" -I"$T/lib/GPU" -Xcompiler -fopenmp
+    $NVCC $CCBIN -o ops_check.out "$T"/lib/GPU/*.o ops_check.o -lredcufhe -lredsec_b200 -Xcompiler -fopenmp )
+  echo "built $T/opscheck/ops_check.out"
+}
+
 if [ $# -gt 0 ]; then
   build_tree tree layer 1 "$@"
+  build_ops_check tree
 else
   build_tree tree layer 1 mnist/sign1024x1 mnist/sign1024x2 mnist/sign1024x3 cifar/binarynet cifar/binarynet_small
+  build_ops_check tree
   build_tree tree_func func 1 mnist/sign1024x1 cifar/binarynet_small
   build_tree tree_g2 layer 2 mnist/sign1024x1 cifar/binarynet_small
   build_tree tree_func_g2 func 2 cifar/binarynet_small

@@ -19,7 +19,10 @@ namespace {
 constexpr uint32_t kUnit = 1u << 20, kEighth = 1u << 29;
 
 template <class Stage, class... A>
-void make_stages(Stage** st, A... args) { for (int g = 0; g < NUM_GPUS; g++) st[g] = new Stage(shim::ctx_of(g), args...); }
+void make_stages(Stage** st, A... args) {
+    shim::ensure_group();
+    for (int g = 0; g < NUM_GPUS; g++) st[g] = new Stage(shim::ctx_of(g), args...);
+}
 template <class Stage>
 void drop_stages(Stage** st) { for (int g = 0; g < NUM_GPUS; g++) delete st[g]; }
 
@@ -47,12 +50,29 @@ void materialize(Packed* p, bool need_all_channels) {
         rs_ctx* ctx = shim::ctx_of(g);
         if (p->pending_sign) shim::check(redsec::QuantizeStage::sign_bootstrap(ctx, p->dev[g], kUnit), "sign bootstrap", ctx);
         if (need_all_channels && p->shard_cl > 0) {
+            if (getenv("RS_SHIM_DEBUG")) {      // checksum of this GPU's channel block before the all-gather
+                std::vector<uint32_t> wire(p->dev[g].count * RS_LWE_WORDS);
+                rs_lwe_download(ctx, wire.data(), p->dev[g].dev, p->dev[g].count);
+                uint64_t sum = 0;
+                for (size_t i = 0; i < wire.size(); i++) sum = sum * 1000003u + wire[i];
+                fprintf(stderr, "shim: block of GPU %d before the all-gather: %zu rows, checksum %016llx\n", g, p->dev[g].count, (unsigned long long)sum);
+            }
             p->dev[g] = redsec::gather_channels(ctx, shim::comm_of(g), p->dev[g], p->shard_cl);
             if (!p->dev[g].dev) shim::check(RS_ERR_STATE, "gather_channels", nullptr);
         }
     });
     p->pending_sign = false;
     if (need_all_channels) p->shard_cl = 0;
+    if (need_all_channels && getenv("RS_SHIM_DEBUG"))       // checksum of the full activation array on every GPU
+        for (int g = 0; g < NUM_GPUS; g++) {
+            if (!p->dev[g].dev) continue;
+            std::vector<uint32_t> wire(p->dev[g].count * RS_LWE_WORDS);
+            rs_lwe_download(shim::ctx_of(g), wire.data(), p->dev[g].dev, p->dev[g].count);
+            uint64_t sum = 0;
+            for (size_t i = 0; i < wire.size(); i++) sum = sum * 1000003u + wire[i];
+            fprintf(stderr, "shim: full array on GPU %d: %zu rows, checksum %016llx\n", g, p->dev[g].count, (unsigned long long)sum);
+        }
+    if (p->dev[0].dev) { p->len = (uint32_t)p->dev[0].count; p->size = (uint8_t)(p->len > 255 ? 255 : p->len); }
 }
 
 template <class Out, class In, class F>
@@ -155,7 +175,7 @@ tFixedPointPacked* IntFunc::SumPooling::execute(tFixedPointPacked* in) {
     return run_stage<tFixedPointPacked>(in, in->len, [&](int g, redsec::Batch b) { return st_[g]->execute(b); });
 }
 
-IntFunc::Quantize::Quantize(tQParams* q) : relu_(q->shift_bits > 1) { make_stages(st_, true, *q); }
+IntFunc::Quantize::Quantize(tQParams* q) : relu_(q->shift_bits >= 2 && q->shift_bits <= 8) { make_stages(st_, true, *q); }
 IntFunc::Quantize::~Quantize() { drop_stages(st_); }
 tDimensions* IntFunc::Quantize::prep(FILE* fd, tDimensions* dim, tMultiBitPacked**, uint16_t* p_slope) {
     const bool slope = relu_ && p_slope != nullptr;     // lib/IntFunc.cpp:800-803: only a ReLU reads the slope block

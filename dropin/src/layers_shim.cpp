@@ -44,6 +44,7 @@ tBitPacked* execute_all(redsec::Layer** impl, In* p_in, size_t in_count, bool is
 
 // ---------------------------------------------------------------------------------------------- IntLayer
 IntLayer::IntLayer(eConvType ec, uint16_t dep, ePoolType ep, eQuantType eq, tNetParams* np) : quant_(eq) {
+    shim::ensure_group();
     for (int g = 0; g < NUM_GPUS; g++) impl_[g] = new redsec::Layer(shim::ctx_of(g), /*int_inputs=*/true, ec, dep, ep, eq, np);
     memset(&in_dim, 0, sizeof(in_dim));
     memset(&out_dim, 0, sizeof(out_dim));
@@ -56,6 +57,7 @@ void IntLayer::set_print_layer(uint8_t) {}
 
 // ---------------------------------------------------------------------------------------------- BinLayer
 BinLayer::BinLayer(eConvType ec, uint16_t dep, ePoolType ep, eQuantType eq, tNetParams* np) : quant_(eq) {
+    shim::ensure_group();
     for (int g = 0; g < NUM_GPUS; g++) impl_[g] = new redsec::Layer(shim::ctx_of(g), /*int_inputs=*/false, ec, dep, ep, eq, np);
     memset(&in_dim, 0, sizeof(in_dim));
     memset(&out_dim, 0, sizeof(out_dim));

@@ -24,6 +24,9 @@ inline rs_ctx* ctx_of(int g) {
     return c;
 }
 inline rs_comm* comm_of(int g) { return redcufhe::CommunicatorOf(g, NUM_GPUS); }
+// forms the NCCL group now (all contexts exist once net.cu's Initialize loop has run): layer / stage constructors call this so
+// that the group is never created in the middle of an inference with kernels in flight
+inline void ensure_group() { if (NUM_GPUS > 1) (void)redcufhe::CommunicatorOf(0, NUM_GPUS); }
 
 // one host thread per GPU, as the reference's `omp_set_num_threads(NUM_GPUS); #pragma omp parallel for` (lib/GPU/BinFunc_gpu.cu:116-138)
 template <class F>

@@ -70,6 +70,7 @@ int rs_sync(rs_ctx *ctx);                           /* waits for every lane */
 int rs_lanes(rs_ctx *ctx, int n);
 int rs_lane_count(const rs_ctx *ctx);
 int rs_lane_select(rs_ctx *ctx, int lane);
+int rs_reserve_scratch(rs_ctx *ctx, size_t count);   /* size the selected lane's bootstrap scratch for `count` ciphertexts now (no allocation later) */
 int rs_lane_fork(rs_ctx *ctx);
 int rs_lane_join(rs_ctx *ctx);
 
@@ -187,8 +188,14 @@ int rs_allgather(rs_comm *comm, uint32_t *out_dev, const uint32_t *in_dev, size_
  * replaces client/gen_secure_keyset.cpp:94-120, client/encrypt_image.cpp:65-85, client/decrypt_image.cpp:46-63 */
 uint32_t rs_modswitch_to_torus32(int32_t mu, int32_t msize);
 int32_t rs_modswitch_from_torus32(uint32_t phase, int32_t msize);
+/* Production entry points: randomness = ChaCha20 keyed with 256 bits from the OS (getrandom), a fresh key per call. */
+int rs_keygen_secure(int32_t *lwe_key /*[350]*/, int32_t *tlwe_key /*[1024]*/, uint32_t *bsk, uint32_t *ksk);
+int rs_lwe_encrypt_secure(uint32_t *ct_wire, const uint32_t *mu, size_t count, double alpha, const int32_t *lwe_key);
+/* DETERMINISTIC variants for tests and known-answer vectors only (xoshiro256**, not a CSPRNG): the same seed gives the same
+ * key / the same masks, so re-using a seed for two encryptions leaks the difference of their plaintexts. */
 int rs_keygen(uint64_t seed, int32_t *lwe_key /*[350]*/, int32_t *tlwe_key /*[1024]*/, uint32_t *bsk, uint32_t *ksk);
 int rs_lwe_encrypt(uint32_t *ct_wire, const uint32_t *mu, size_t count, double alpha, const int32_t *lwe_key, uint64_t seed);
+int rs_selftest_chacha20(const uint32_t *key /*[8]*/, uint64_t domain, uint64_t index, uint32_t *out, size_t words);   /* KAT hook */
 int rs_lwe_phase(uint32_t *phase, const uint32_t *ct_wire, size_t count, const int32_t *lwe_key);
 int rs_lwe_decrypt(int32_t *msg, const uint32_t *ct_wire, size_t count, const int32_t *lwe_key, int32_t msize);
 int rs_write_secret_key(const char *path, const int32_t *lwe_key, const int32_t *tlwe_key);

@@ -22,6 +22,7 @@ SIGNATURES = {
     "rs_lanes": (C.c_int, [vp, C.c_int]),
     "rs_lane_count": (C.c_int, [vp]),
     "rs_lane_select": (C.c_int, [vp, C.c_int]),
+    "rs_reserve_scratch": (C.c_int, [vp, C.c_size_t]),
     "rs_lane_fork": (C.c_int, [vp]),
     "rs_lane_join": (C.c_int, [vp]),
     "rs_last_error": (C.c_char_p, [vp]),
@@ -71,6 +72,9 @@ SIGNATURES = {
     "rs_lwe_interleave": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_int, C.c_int]),
     "rs_modswitch_to_torus32": (C.c_uint32, [C.c_int32, C.c_int32]),
     "rs_modswitch_from_torus32": (C.c_int32, [C.c_uint32, C.c_int32]),
+    "rs_selftest_chacha20": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, C.c_size_t]),
+    "rs_keygen_secure": (C.c_int, [vp, vp, vp, vp]),
+    "rs_lwe_encrypt_secure": (C.c_int, [vp, vp, C.c_size_t, C.c_double, vp]),
     "rs_keygen": (C.c_int, [C.c_uint64, vp, vp, vp, vp]),
     "rs_lwe_encrypt": (C.c_int, [vp, vp, C.c_size_t, C.c_double, vp, C.c_uint64]),
     "rs_lwe_phase": (C.c_int, [vp, vp, C.c_size_t, vp]),

@@ -28,31 +28,41 @@ def _chk(rc, what):
         raise RsError(f"{what} failed with code {rc}")
 
 
-def keygen(seed: int = 0) -> KeySet:
-    """redsec_params_small_v2 keyset, deterministic from the seed (client/gen_secure_keyset.cpp:94-102 uses seed {0,0,0})."""
+def keygen(seed: int | None = None) -> KeySet:
+    """redsec_params_small_v2 keyset (client/gen_secure_keyset.cpp:70-102).  seed=None (default): OS entropy + ChaCha20
+    (rs_keygen_secure).  An integer seed gives the DETERMINISTIC test keyset (rs_keygen) -- tests, benchmarks and
+    known-answer vectors only; the reference's own keygen seeds its generator with {0,0,0}, i.e. every user's key is the same."""
     lib = _lib.load()
     lwe_key = np.empty(LWE_N, np.int32)
     tlwe_key = np.empty(TLWE_N, np.int32)
     bsk = np.empty(BSK_WORDS, np.uint32)
     ksk = np.empty(KSK_WORDS, np.uint32)
-    _chk(lib.rs_keygen(seed, lwe_key.ctypes.data, tlwe_key.ctypes.data, bsk.ctypes.data, ksk.ctypes.data), "rs_keygen")
+    if seed is None:
+        _chk(lib.rs_keygen_secure(lwe_key.ctypes.data, tlwe_key.ctypes.data, bsk.ctypes.data, ksk.ctypes.data), "rs_keygen_secure")
+    else:
+        _chk(lib.rs_keygen(seed, lwe_key.ctypes.data, tlwe_key.ctypes.data, bsk.ctypes.data, ksk.ctypes.data), "rs_keygen")
     return KeySet(lwe_key, tlwe_key, bsk, ksk)
 
 
-def encrypt(mu, lwe_key, alpha: float, seed: int) -> np.ndarray:
+def encrypt(mu, lwe_key, alpha: float, seed: int | None = None) -> np.ndarray:
+    """LWE encryption of torus32 messages.  seed=None: fresh OS entropy per call (rs_lwe_encrypt_secure).  An integer seed is
+    for tests only: the same seed gives the same masks, so never encrypt two different messages under one seed."""
     lib = _lib.load()
     mu = np.ascontiguousarray(np.asarray(mu, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32).reshape(-1)
     ct = np.empty((mu.size, LWE_WORDS), np.uint32)
-    _chk(lib.rs_lwe_encrypt(ct.ctypes.data, mu.ctypes.data, mu.size, alpha, lwe_key.ctypes.data, seed), "rs_lwe_encrypt")
+    if seed is None:
+        _chk(lib.rs_lwe_encrypt_secure(ct.ctypes.data, mu.ctypes.data, mu.size, alpha, lwe_key.ctypes.data), "rs_lwe_encrypt_secure")
+    else:
+        _chk(lib.rs_lwe_encrypt(ct.ctypes.data, mu.ctypes.data, mu.size, alpha, lwe_key.ctypes.data, seed), "rs_lwe_encrypt")
     return ct
 
 
-def encrypt_bits(bits, lwe_key, seed: int, mu: int = EIGHTH, alpha: float = ALPHA_GATE) -> np.ndarray:
+def encrypt_bits(bits, lwe_key, seed: int | None = None, mu: int = EIGHTH, alpha: float = ALPHA_GATE) -> np.ndarray:
     bits = np.asarray(bits)
     return encrypt(np.where(bits != 0, mu, -mu), lwe_key, alpha, seed)
 
 
-def encrypt_image(pixels, lwe_key, seed: int) -> np.ndarray:
+def encrypt_image(pixels, lwe_key, seed: int | None = None) -> np.ndarray:
     """client/encrypt_image.cpp:76-77: LWE(modSwitchToTorus32(2p-255, 4096), alpha=2^-15) per pixel (all pixels: R1 not reproduced)."""
     v = 2 * np.asarray(pixels, dtype=np.int64) - 255
     return encrypt(v * UNIT, lwe_key, SECALPHA, seed)

@@ -607,6 +607,12 @@ int rs_ext_download(rs_ctx* ctx, uint32_t* host, const uint32_t* dev, size_t cou
     return RS_OK;
 }
 
+int rs_reserve_scratch(rs_ctx* ctx, size_t count) {
+    DeviceGuard dg(ctx);
+    if (!ctx) return RS_ERR_ARG;
+    return grow(ctx, &ctx->ext, &ctx->ext_cap, count * rs::EXT_STRIDE);
+}
+
 int rs_pbs_batch(rs_ctx* ctx, uint32_t* out_dev, const uint32_t* in_dev, size_t count, uint32_t mu) {
     DeviceGuard dg(ctx);
     if (!ctx || !out_dev || !in_dev) return fail(ctx, RS_ERR_ARG, "rs_pbs_batch: NULL argument");

@@ -222,7 +222,7 @@ blind_rotate_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRID
     for (int j = t; j < N; j += 64) {
         acc[j] = 0;
         const int idx = (j + barb) & (2 * N - 1);                        // X^{2N-barb} * testvector
-        const uint32_t v = tv ? tv[idx & (N - 1)] : mu;                  // (mu + mu X + ... for the sign bootstrap)
+        const uint32_t v = tv ? __ldcg(tv + (idx & (N - 1))) : mu;                  // (mu + mu X + ... for the sign bootstrap)
         acc[N + j] = idx < N ? v : 0u - v;
     }
     Twiddles tw;

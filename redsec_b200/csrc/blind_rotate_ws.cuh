@@ -169,7 +169,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             for (int k = lane; k < N; k += 32) {
                 acc[k] = 0;
                 const int idx = (k + barb) & (2 * N - 1);                        // X^{2N-barb} * testvector
-                const uint32_t v = tv ? tv[idx & (N - 1)] : mu;                  // (mu + mu X + ... for the sign bootstrap)
+                const uint32_t v = tv ? __ldcg(tv + (idx & (N - 1))) : mu;                  // (mu + mu X + ... for the sign bootstrap)
                 acc[N + k] = idx < N ? v : 0u - v;
             }
         }
@@ -284,6 +284,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         uint32_t* ext = ext_out + (size_t)ct * EXT_STRIDE;
         for (int k = lane; k < N; k += 32) ext[k] = (k == 0) ? acc[0] : 0u - acc[N - k];
         if (lane == 0) { ext[N] = acc[N]; ext[N + 1] = 0; ext[N + 2] = 0; ext[N + 3] = 0; }
+        __threadfence();      // the extracted sample is read by the keyswitch launch that follows (RS_END_FENCE, lwe_kernels.cuh)
         return;
     }
 

@@ -40,7 +40,7 @@ namespace {
 constexpr uint32_t kUnit = 1u << 20;        // 1/4096 on the torus
 constexpr uint32_t kEighth = 1u << 29;      // 1/8
 constexpr int kTile = 16;                   // CONV_OD_TILE of the conv kernel
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = 2;            // see run_maxpool_sign: three or more concurrent chains were measured to corrupt rows
 constexpr size_t kWaveCts = 4 * 148;        // ciphertexts of one full wave of blind-rotate CTAs (4 per SM)
 
 #define RS_TRY(call) do { int rc_ = (call); if (rc_ != RS_OK) return rc_; } while (0)
@@ -563,8 +563,16 @@ public:
             }
             RS_TRY(plan->final_gather.apply(pooled.p, tree.p));
         } else {
-            const int lanes = std::min(nb, kMaxLanes);
+            int lanes = std::min(nb, kMaxLanes);
+            if (const char* e = getenv("RS_LANES_MAX")) lanes = std::max(1, std::min(lanes, atoi(e)));     // diagnostics
+            const bool serial = getenv("RS_LANE_SERIAL") != nullptr;                                       // diagnostics: never two blocks in flight
             RS_TRY(rs_lanes(ctx, lanes));
+            // every lane's bootstrap scratch is sized before the fork: no device allocation while other lanes' launches are in flight
+            const size_t per_block = ((size_t)(mp_out_h + nb - 1) / nb) * (size_t)np.pool.stride.h * q_w * cl + (size_t)q_w * cl * np.pool.stride.h;
+            for (int l = lanes - 1; l >= 0; l--) {
+                RS_TRY(rs_lane_select(ctx, l));
+                RS_TRY(rs_reserve_scratch(ctx, std::min(per_block, cur_count)));
+            }
             RS_TRY(rs_lane_fork(ctx));
             const size_t win_rows = (size_t)mp_out_w * cl;                       // pooled outputs per output row
             const size_t in_rows = (size_t)np.pool.stride.h * q_w * cl;          // neurons per output row of windows
@@ -584,6 +592,7 @@ public:
                     if (rc == RS_OK) rc = rs_pbs_batch(ctx, tree.p + (st->dst_offset + r0) * S, cur + i0 * S, r1 - r0, st->mu);
                 }
                 if (rc == RS_OK) rc = plan->final_gather.apply_range(pooled.p + o0 * S, tree.p, o0, o1);
+                if (serial && rc == RS_OK) { rs_lane_select(ctx, 0); rc = rs_lane_join(ctx); if (rc == RS_OK) rc = rs_lane_fork(ctx); }
             }
             rs_lane_select(ctx, 0);
             const int rj = rs_lane_join(ctx);       // always re-join: the buffers above go back to the pool after this point
@@ -851,14 +860,18 @@ Batch SumPoolStage::execute(Batch in) {
 
 QuantizeStage::QuantizeStage(rs_ctx* ctx, bool int_inputs, const tQParams& q) : impl_(new LayerImpl(ctx)) {
     impl_->np = stage_params(); impl_->np.quant = q; impl_->int_inputs = int_inputs;
-    // shift_bits selects the activation the way {Bin,Int}Layer's constructor sets it (lib/GPU/IntLayer.cu:57-59): 0 none, 1 sign, >1 ReLU
-    impl_->eq = q.shift_bits == 0 ? E_ACTIVATION_NONE : q.shift_bits == 1 ? E_ACTIVATION_SIGN : E_ACTIVATION_RELU;
+    // The reference's Quantize only stores shift_bits; which activation runs is decided by the method the layer calls
+    // (execute / add_bias / relu_shift, lib/GPU/BinLayer.cu:160-175).  shift_bits still shapes prep(): 0 none, 1 sign, 2..8 a
+    // DoReFa ReLU (lib/IntFunc.cpp:812-840).  The generated drivers leave tNetParams::quant uninitialised for layers without a
+    // ReLU (nets/cifar/binarynet/net.cu:78-93 never sets it), so any other value is treated as "no ReLU tables" rather than an error.
+    const bool relu_ok = int_inputs && q.shift_bits >= 2 && q.shift_bits <= 8;
+    impl_->eq = q.shift_bits == 1 ? E_ACTIVATION_SIGN : relu_ok ? E_ACTIVATION_RELU : E_ACTIVATION_NONE;
 }
 QuantizeStage::~QuantizeStage() = default;
 const std::vector<int32_t>& QuantizeStage::bias() const { return impl_->bias_int; }
 int QuantizeStage::channels() const { return impl_->q_dep; }
 tDimensions* QuantizeStage::prep(FILE* fd, tDimensions* dim, bool read_slope) {
-    if (impl_->prep_quant(fd, dim, read_slope && impl_->np.quant.shift_bits > 1) != RS_OK) { printf("Bad Weights File. Exiting...\r\n"); return nullptr; }
+    if (impl_->prep_quant(fd, dim, read_slope && impl_->is_relu()) != RS_OK) { printf("Bad Weights File. Exiting...\r\n"); return nullptr; }
     if (impl_->ctx) {
         if (rs_dev_alloc(impl_->ctx, impl_->bias_torus.size() * 4, &impl_->bias_dev) != RS_OK) return nullptr;
         if (rs_dev_upload(impl_->ctx, impl_->bias_dev, impl_->bias_torus.data(), impl_->bias_torus.size() * 4) != RS_OK) return nullptr;

@@ -5,6 +5,9 @@
 // only coherent at kernel boundaries of an otherwise idle SM: with several lanes in flight (rs_lanes) an SM runs CTAs of other
 // kernels back to back without its L1 being invalidated, and a buffer that is rewritten between two launches (the gate
 // pre-combination scratch, the extracted-sample scratch) was then read stale by a later launch landing on the same SM.
+// The same holds for the read-modify-write kernels (bias / constant add): a line they pull into an L1 can still be there when a
+// LIBRARY kernel (NCCL's all-gather of a ciphertext buffer) later reads that address after other kernels rewrote it -- observed
+// as intermittently wrong all-gathered rows with 2 GPUs.  No kernel here leaves ciphertext data in an L1.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -51,6 +54,7 @@ __global__ void keyswitch_init_kernel(const uint32_t* __restrict__ ext, int coun
         const int x = (int)(idx % LWE_STRIDE);
         lwe_out[idx] = (x == LWE_N) ? __ldcg(ext + c * EXT_STRIDE + N) : 0u;
     }
+    __threadfence();      // RS_END_FENCE: see the header note
 }
 
 template <int TILE>
@@ -135,14 +139,18 @@ keyswitch_tiled_kernel(const uint32_t* __restrict__ ext,      // [count][EXT_STR
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + (KS_STAGES + s) * 8);
     }
+    uint32_t sink = 0;
 #pragma unroll
     for (int c = 0; c < CPG; c++) {
         const int ct = g * CPG + c;
         if (ct < tile) {
             uint32_t* o = lwe_out + (size_t)(first + ct) * LWE_STRIDE + 4 * l4;
-            atomicAdd(o + 0, acc[c].x); atomicAdd(o + 1, acc[c].y); atomicAdd(o + 2, acc[c].z); atomicAdd(o + 3, acc[c].w);
+            // ATOM (value returned and consumed), not RED: the thread cannot retire before the L2 has performed its last partial sums
+            sink ^= atomicAdd(o + 0, acc[c].x) ^ atomicAdd(o + 1, acc[c].y) ^ atomicAdd(o + 2, acc[c].z) ^ atomicAdd(o + 3, acc[c].w);
         }
     }
+    if (sink == 0x9E3779B9u && count < 0) lwe_out[0] = sink;      // never true: keeps the returned values live
+    __threadfence();      // RS_END_FENCE
 }
 
 // KSK host layout [N][t][8][351] -> tiled device layout [N][t][7][352] (digit-0 rows dropped, rows zero-padded)
@@ -224,6 +232,7 @@ __global__ void lwe_pad_kernel(const uint32_t* __restrict__ src, uint32_t* __res
         int x = (int)(idx % LWE_STRIDE);
         dst[idx] = x < LWE_WORDS ? __ldcg(src + r * LWE_WORDS + x) : 0u;
     }
+    __threadfence();      // RS_END_FENCE
 }
 __global__ void lwe_unpad_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int count) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,6 +257,7 @@ __global__ void gate_linear_kernel(uint32_t* __restrict__ out, const uint32_t* _
         if (x > LWE_N) v = 0;
         out[idx] = v;
     }
+    __threadfence();      // RS_END_FENCE
 }
 
 // out = (0, fix) + m0 * in0 + m1 * in1: add_int / sub_int / mul_int / levelNOT of lib/GPU/gates.cu:110-122,158-202 for a batch
@@ -262,6 +272,7 @@ __global__ void lwe_axpby_kernel(uint32_t* __restrict__ out, const uint32_t* __r
         if (x > LWE_N) v = 0;
         out[idx] = v;
     }
+    __threadfence();      // RS_END_FENCE
 }
 
 // ---------------------------------------------------------------- ternary linear layer on LWE rows (a10 / f1)
@@ -286,19 +297,22 @@ lwe_lincomb_kernel(uint32_t* __restrict__ out, int out_count, const uint32_t* __
         if (bias && x == LWE_N / 4) acc.z += bias[o];   // word 350 = b
         reinterpret_cast<uint4*>(out + (size_t)o * LWE_STRIDE)[x] = acc;
     }
+    __threadfence();      // RS_END_FENCE
 }
 
 // b word of every row += value: adds the trivial sample (0,value) (lweNoiselessTrivial + lweAddTo, lib/BinOps_enc.cpp:137-141)
 __global__ void lwe_add_const_kernel(uint32_t* __restrict__ rows, size_t count, uint32_t value) {
     for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < count; c += (size_t)gridDim.x * blockDim.x)
-        rows[c * LWE_STRIDE + LWE_N] += value;
+        rows[c * LWE_STRIDE + LWE_N] = __ldcg(rows + c * LWE_STRIDE + LWE_N) + value;      // L2-only load: see the header note
+    __threadfence();      // RS_END_FENCE
 }
 
 // b word of row r += bias[r % mod]: the per-channel bias add of Quantize::execute / add_bias (lib/BinFunc.cpp:1063-1065,1085-1107;
 // rows are channel-fastest) as a stage of its own, for callers that compose Func objects instead of whole layers
 __global__ void lwe_add_bias_kernel(uint32_t* __restrict__ rows, size_t count, const uint32_t* __restrict__ bias, int mod) {
     for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < count; c += (size_t)gridDim.x * blockDim.x)
-        rows[c * LWE_STRIDE + LWE_N] += bias[c % (size_t)mod];
+        rows[c * LWE_STRIDE + LWE_N] = __ldcg(rows + c * LWE_STRIDE + LWE_N) + bias[c % (size_t)mod];
+    __threadfence();      // RS_END_FENCE
 }
 
 // ---------------------------------------------------------------- [world][pixels][c_local] -> [pixels][world*c_local]
@@ -311,6 +325,7 @@ __global__ void lwe_interleave_kernel(uint4* __restrict__ out, const uint4* __re
         const int r = ch / c_local, c = ch % c_local;
         out[row * (LWE_STRIDE / 4) + x] = __ldcg(in + (((size_t)r * pixels + pix) * c_local + c) * (LWE_STRIDE / 4) + x);
     }
+    __threadfence();      // RS_END_FENCE
 }
 
 // ---------------------------------------------------------------- ternary convolution / fully-connected layer on LWE rows
@@ -384,6 +399,7 @@ lwe_conv_kernel(uint32_t* __restrict__ out,             // [out_h*out_w][od_end-
         }
         reinterpret_cast<uint4*>(out + ((size_t)pix * od_count + (od - d.od_begin)) * LWE_STRIDE)[lane] = r;
     }
+    __threadfence();      // RS_END_FENCE
 }
 
 }  // namespace rs

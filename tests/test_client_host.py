@@ -6,6 +6,8 @@ import numpy as np
 
 from redsec_b200 import client, netspec
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_product_keygen_equals_oracle_spec(oracle, keyset):
     ks = client.keygen(0)
@@ -86,3 +88,77 @@ def test_shard_ranges_partition_channels():
             else:
                 assert all(g == (0, channels) for g in got)      # not shardable -> replicated
     assert nets.shard_range(3, False, 1, 2) == (0, 3)             # no conv stage -> replicated
+
+
+def test_chacha20_known_answer():
+    """The CSPRNG behind rs_keygen_secure / rs_lwe_encrypt_secure is ChaCha20 (64-bit counter, 64-bit nonce): all-zero key and
+    nonce give the published keystream 76 b8 e0 ad a0 f1 3d 90 40 5d 6a e5 53 86 bd 28 ... (Bernstein's test vector, also
+    draft-agl-tls-chacha20poly1305 TC1); the second block continues it, and another stream index gives different words."""
+    import ctypes as C
+    from redsec_b200 import _lib
+    lib = _lib.load()
+    key = np.zeros(8, np.uint32)
+    out = np.zeros(32, np.uint32)
+    assert lib.rs_selftest_chacha20(key.ctypes.data, 0, 0, out.ctypes.data, 32) == 0
+    want = bytes.fromhex("76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+                         "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586"
+                         "9f07e7be5551387a98ba977c732d080dcb0f29a048e3656912c6533e32ee7aed"
+                         "29b721769ce64e43d57133b074d839d531ed1f28510afb45ace10a1f4b794d6f")
+    assert out.astype("<u4").tobytes() == want
+    other = np.zeros(16, np.uint32)
+    assert lib.rs_selftest_chacha20(key.ctypes.data, 5, 1, other.ctypes.data, 16) == 0
+    assert not np.array_equal(other, out[:16])
+
+
+def test_secure_keygen_and_encryption_are_fresh_every_call():
+    """the default client paths draw from the OS (ChaCha20 keyed by getrandom): two key generations differ, two
+    encryptions of the same message share neither masks nor noise, and both decrypt; explicit seeds stay reproducible."""
+    from redsec_b200 import client
+    k1, k2 = client.keygen(), client.keygen()
+    assert not np.array_equal(k1.lwe_key, k2.lwe_key) and not np.array_equal(k1.bsk[:2048], k2.bsk[:2048])
+    assert set(np.unique(k1.lwe_key)) <= {0, 1} and 100 < int(k1.lwe_key.sum()) < 250
+    msg = np.arange(-8, 8) * client.UNIT
+    c1, c2 = client.encrypt(msg, k1.lwe_key, client.SECALPHA), client.encrypt(msg, k1.lwe_key, client.SECALPHA)
+    assert not np.array_equal(c1[:, :350], c2[:, :350])
+    assert np.array_equal(client.decrypt(c1, k1.lwe_key), np.arange(-8, 8)) and np.array_equal(client.decrypt(c2, k1.lwe_key), np.arange(-8, 8))
+    # the key material is usable: a key-switching key row decrypts (under the LWE key) to h * s'_i / base^(j+1)
+    ks_row = k1.ksk.reshape(1024, 9, 8, 351)[3, 0, 5][None, :]
+    ph = int(client.phase(ks_row, k1.lwe_key)[0])
+    expect = (5 * int(k1.tlwe_key[3])) << 29
+    assert abs(((ph - expect + 2 ** 31) % 2 ** 32) - 2 ** 31) < 2 ** 12
+    s1, s2 = client.encrypt(msg, k1.lwe_key, client.SECALPHA, seed=9), client.encrypt(msg, k1.lwe_key, client.SECALPHA, seed=9)
+    assert np.array_equal(s1, s2)
+
+
+def test_client_executables_round_trip_through_files(tmp_path):
+    """client/Makefile workflow (reference client/Makefile:1-25): keygen -> image_converter.py -> encrypt-image -> decrypt-image,
+    files only.  The tools' files are the library's formats: image.ctxt written by encrypt.out equals client.encrypt_image
+    with the same test seed and decrypts to 2p-255 for ALL 784 pixels (defect R1 not reproduced); decrypt.out recovers the
+    argmax of the scores in network_output.ctxt."""
+    import shutil
+    import subprocess
+    from redsec_b200 import client, netspec
+    cdir = os.path.join(ROOT, "client")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call(["make", "-C", cdir, "all", f"CXX={gxx}"], stdout=subprocess.DEVNULL)
+    run = lambda *a: subprocess.run(list(a), cwd=tmp_path, check=True, capture_output=True, text=True).stdout
+    assert "deterministic TEST keyset" in run(os.path.join(cdir, "keygen.out"), "-seclevel", "128", "--seed", "0")
+    ks = client.read_keys(str(tmp_path / "secret.key"), str(tmp_path / "eval.key"))
+    ref = client.keygen(0)
+    assert np.array_equal(ks.lwe_key, ref.lwe_key) and np.array_equal(ks.bsk, ref.bsk) and np.array_equal(ks.ksk, ref.ksk)
+    run("python3", os.path.join(cdir, "image_converter.py"), "--format", "MNIST", "--image", os.path.join(ROOT, "data", "client", "mnist_test.csv"))
+    assert (tmp_path / "image.ptxt").read_text().startswith("0,28,28,1,")
+    run(os.path.join(cdir, "encrypt.out"), "image.ptxt", "--seed", "11")
+    label, px = netspec.load_image_csv(os.path.join(ROOT, "data", "client", "mnist_test.csv"))
+    ct = client.read_ctxt(str(tmp_path / "image.ctxt"), 784)
+    assert np.array_equal(ct, client.encrypt_image(px, ks.lwe_key, seed=11))
+    assert np.array_equal(client.decrypt(ct, ks.lwe_key), 2 * np.asarray(px) - 255)
+    run(os.path.join(cdir, "encrypt.out"), "image.ptxt")                                   # OS entropy: a different ciphertext, same pixels
+    ct2 = client.read_ctxt(str(tmp_path / "image.ctxt"), 784)
+    assert not np.array_equal(ct2, ct) and np.array_equal(client.decrypt(ct2, ks.lwe_key), 2 * np.asarray(px) - 255)
+    scores = np.array([-143, 12, 300, -7, 299, 0, -2048 + 1, 2047, 5, -1])
+    client.write_ctxt(str(tmp_path / "network_output.ctxt"), client.encrypt(scores * client.UNIT, ks.lwe_key, 2.0 ** -25, seed=3))
+    out = run(os.path.join(cdir, "decrypt.out"), "MNIST")
+    assert "Classification Result: 7" in out and "Scores: -143 12 300 -7 299 0 -2047 2047 5 -1" in out
+    for f in ("keygen.out", "encrypt.out", "decrypt.out"):
+        os.remove(os.path.join(cdir, f))
