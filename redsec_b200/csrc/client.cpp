@@ -10,7 +10,7 @@
 //     (getrandom) drives ChaCha20, one independent stream per (purpose, index) through the nonce; nothing is derived from a
 //     caller-supplied integer, so two encryptions never share masks or noise.
 //   * rs_keygen(seed) / rs_lwe_encrypt(..., seed): a documented DETERMINISTIC generator (splitmix64-seeded xoshiro256**,
-//     Box-Muller; spec in oracle/tfhe_oracle.c) for tests and known-answer vectors ONLY -- xoshiro is not a CSPRNG, and
+//     Box-Muller; the stream specification is in DESIGN.md 6) for tests and known-answer vectors ONLY -- xoshiro is not a CSPRNG, and
 //     re-using a seed for two encryptions re-uses their masks (b1 - b2 then reveals mu1 - mu2).  Never use it for real data.
 // Upstream TFHE's std::default_random_engine stream (seeded {0,0,0} by client/gen_secure_keyset.cpp:99, i.e. the same key for
 // every user) is not reproduced: there is no upstream fixture to compare against.  File layouts are this repo's own and are self-round-trip
