@@ -23,8 +23,26 @@ class LayerParams(C.Structure):
         "e_bias", "shift_bits", "version")]
 
 
+class _DryEngine:
+    """Stands in for an Engine when a net is only prepared and asked for its shapes / shard plan (no device, no context)."""
+    ctx = None
+    device = -1
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise RsError(f"redsec_b200 error {rc}")
+
+    def _adopt(self, child):
+        pass
+
+
 class EncryptedNet:
-    def __init__(self, eng: Engine, spec: dict):
+    def __init__(self, eng: Engine | None, spec: dict):
+        """eng=None: a dry net (host logic only: layer_info, shard_plan, bootstraps); running it needs an Engine."""
+        eng = eng if eng is not None else _DryEngine()
         self.eng, self.spec, self.lib = eng, spec, eng.lib
         self.net = self.lib.rs_net_create(eng.ctx)
         if not self.net:
@@ -57,7 +75,7 @@ class EncryptedNet:
 
     def __del__(self):      # a net dropped without close() must still give its context reference back
         try:
-            if self.eng.ctx:
+            if self.eng.ctx or isinstance(self.eng, _DryEngine):
                 self.close()
         except Exception:
             pass

@@ -47,6 +47,41 @@ def _worker(rank, world, port, tmpdir):
     dist.all_gather(g0, torch.from_numpy(mine0.astype(np.int64)))
     cat0 = torch.cat(g0).numpy().astype(np.uint32)
     ok = ok and np.array_equal(cat0[nets.interleave_index(64, 3, 1)], full0)
+    # the library's own shard plan (rs_net_shard_plan on a net without a device context) drives a whole sharded forward of the
+    # tiny net: per layer, this rank's block of the oracle's layer output -> all-gather -> (interleave) must equal the full output
+    dry = nets.EncryptedNet(None, spec)
+    x = ct
+    modes = []
+    for li, Lr in enumerate(layers):
+        plan = dry.shard_plan(li, world)
+        info = dry.layer_info(li)
+        modes.append(plan["mode"])
+        lin = LO.enc_linear(Lr, x)                            # bootstrap-free stand-in for the layer (the exchange logic is what is tested)
+        if Lr.has_maxpool:                                    # pooled layers exchange AFTER the pool: emulate by taking the window corner
+            oh, ow = Lr.mp_geom[4], Lr.mp_geom[5]
+            lin = lin.reshape(Lr.q_dims + (351,))[0:2 * oh:2, 0:2 * ow:2].reshape(-1, 351)
+        assert lin.shape[0] == info["out_count"]
+        ch = info["channels"]
+        if plan["mode"] == 0:
+            out_l = lin
+        elif plan["mode"] == 2:                               # pixel blocks: gathered row blocks are already canonical
+            per_r = plan["rows_per_rank"]
+            mine_l = lin[rank * per_r:(rank + 1) * per_r].copy()
+            g = [torch.empty(mine_l.shape, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(mine_l.astype(np.int64)))
+            out_l = torch.cat(g).numpy().astype(np.uint32)
+        else:                                                 # channel blocks
+            cl = plan["c_local"]
+            assert cl * world == ch and plan["rows_per_rank"] * world == info["out_count"]
+            mine_l = lin.reshape(-1, ch, 351)[:, rank * cl:(rank + 1) * cl].reshape(-1, 351).copy()
+            g = [torch.empty(mine_l.shape, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(mine_l.astype(np.int64)))
+            cat_l = torch.cat(g).numpy().astype(np.uint32)
+            out_l = cat_l[nets.interleave_index(lin.shape[0] // ch, cl, world)]
+        ok = ok and np.array_equal(out_l, lin)
+        x = lin
+    ok = ok and modes == [2, 1, 1, 1, 1]                      # input layer by pixel, conv / FC layers by channel (10 % 2 == 0)
+    dry.close()
     flag = torch.tensor([int(ok)])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
@@ -61,3 +96,23 @@ def test_sharded_layer_gather_world2(tmp_path):
     netspec.write_random_weights(spec, str(tmp_path / "w.dat"), seed=9, p_zero=0.2)
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+def test_shard_plan_of_the_shipped_nets():
+    """rs_net_shard_plan (host logic, no device): how every layer of the BASELINE nets splits over 2 / 4 / 8 GPUs -- conv / FC
+    layers by output-channel block, conv-less input layers by output pixel, whatever does not divide stays whole."""
+    from redsec_b200 import netspec, nets
+    cifar = nets.EncryptedNet(None, netspec.NETS["cifar/binarynet"]())
+    assert cifar.bootstraps() == 635904
+    for world in (2, 4, 8):
+        plans = [cifar.shard_plan(i, world) for i in range(cifar.num_layers)]
+        assert [p["mode"] for p in plans] == [2, 1, 1, 1, 1, 1, 1, 1, 1, 0 if 10 % world else 1]
+        assert plans[1]["rows_per_rank"] == 32 * 32 * 128 // world and plans[1]["c_local"] == 128 // world
+        assert plans[2]["rows_per_rank"] == 16 * 16 * 128 // world          # exchanged AFTER the max-pool: 4x fewer ciphertexts
+        assert plans[0]["rows_per_rank"] == 3072 // world
+    cifar.close()
+    mnist = nets.EncryptedNet(None, netspec.NETS["mnist/sign1024x1"]())
+    assert [mnist.shard_plan(i, 8)["mode"] for i in range(3)] == [0, 1, 0]     # 196 pooled pixels do not divide by 8; FC10 neither
+    assert [mnist.shard_plan(i, 2)["mode"] for i in range(3)] == [2, 1, 1]
+    assert [mnist.shard_plan(i, 1)["mode"] for i in range(3)] == [0, 0, 0]
+    mnist.close()
