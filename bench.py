@@ -305,7 +305,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         br_avg_s = br_ms / max(br_n, 1) * 1e-3
         achieved_tflops = FLOP_PER_PBS * G / br_avg_s / 1e12
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
@@ -334,13 +334,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "frac": achieved_tflops / fp64_peak, "traffic": traffic,
                          "kernel": "blind_rotate_ws_kernel", "launch_ms": br_avg_s * 1e3, "launches": int(br_n),
                          "algorithmic_flop_per_launch": FLOP_PER_PBS * G,
-                         "peak_source": "measured live by rs_fp64_peak (dependent-free DFMA loop with constant operands, all SMs); MEASURED_PEAKS.json has no FP64 figure",
+                         "peak_source": "measured live by rs_fp64_peak: unrolled dependent-free DFMA loop (two register operands + immediate, 32 DFMA per trip), best of 12 / 16 / 32 warps per SM; MEASURED_PEAKS.json has no FP64 figure (nominal 64 DFMA/clk/SM x 148 x 1.965 GHz = 37.2)",
                          "peak_three_register_fma": fp64_peak3,
                          "frac_of_three_register_fma_peak": achieved_tflops / fp64_peak3,
                          "note": "a DFMA with three distinct register operands issues every 3 cycles instead of 2 (register-file bound, scripts/probes/fp64_probe2.cu); "
                                  "peak_three_register_fma is that rate measured live, the ceiling of the MAC and twiddle FMAs",
-                         "traffic_note": "DRAM bytes of one 2^16-ciphertext blind-rotate launch from ncu (profiles/r1_traffic.json); the Fourier BSK is re-streamed "
-                                         "about once per 2 waves of CTAs; the algorithmic bytes count it once; HBM use stays below 1 % of peak either way",
+                         "traffic_source": "static: read from profiles/r2_traffic.json, one ncu capture of a 2^16-ciphertext launch (a bench run is never profiled)",
+                         "traffic_note": "DRAM bytes of one 2^16-ciphertext blind-rotate launch; the Fourier BSK (114.7 MB) is re-streamed from DRAM about twice per wave "
+                                         "of CTAs; the algorithmic bytes count it once; HBM use stays below 1 % of peak either way",
                          "hbm": {"algorithmic_bytes_per_launch": BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4),
                                  "achieved_gbs": (BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4)) / br_avg_s / 1e9,
                                  "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
