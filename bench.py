@@ -345,9 +345,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "hbm": {"algorithmic_bytes_per_launch": BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4),
                                  "achieved_gbs": (BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4)) / br_avg_s / 1e9,
                                  "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                         "keyswitch": {"kernel": "keyswitch_tiled_kernel", "launch_ms": ks_ms / max(ks_n / 2, 1),
-                                       "bound": "shared-memory bandwidth", "smem_read_bytes_per_launch": G * 9216 * 7 / 8 * 1408,
-                                       "l2_to_smem_bytes_per_launch": (G // 64) * KSK_TILED_BYTES},
+                         "keyswitch": {"kernel": "keyswitch_mma_kernel (tcgen05.mma kind::i8, one-hot x u8-limb key, exact) + transpose prep" if G >= 2048 else "keyswitch_tiled_kernel",
+                                       "launch_ms": ks_ms / max(ks_n / 2, 1),
+                                       "bound": "tensor (int8) / L2->smem key stream" if G >= 2048 else "shared-memory bandwidth",
+                                       "tensor_ops_per_launch": 2.0 * G * 73728 * 1408,
+                                       "achieved_tops": 2.0 * G * 73728 * 1408 / (ks_ms / max(ks_n / 2, 1) * 1e-3) / 1e12 if G >= 2048 else None,
+                                       "peak_tops_nominal_int8_dense": 4500.0,
+                                       "peak_note": "MEASURED_PEAKS.json has no int8 figure; nominal dense int8 4.5 POP/s (2x the bf16 figure, whose measured burst is %.0f TF/s)" % peaks.get("bf16_tflops", 0.0),
+                                       "l2_to_smem_bytes_per_launch": (G // 256) * 6 * 2304 * 8192 if G >= 2048 else (G // 64) * KSK_TILED_BYTES,
+                                       "note": "the one-hot GEMM executes 8x the additions of the gather formulation (digit 0..7 slots); the gather kernel needs 24.9 ms per 2^16"},
                          "step_share": {"blind_rotate_ms": br_ms / args.steps, "keyswitch_ms": ks_ms / args.steps,
                                         "linear_ms": lin_ms / args.steps}},
             "cpu_baseline": cpu,

@@ -256,7 +256,7 @@ uint64_t rs_launch_count(const rs_ctx *ctx);        /* kernels launched by this 
 int rs_fp64_peak(rs_ctx *ctx, double *tflops);      /* dependent-free DFMA loop on all SMs: the FP64 roofline denominator */
 int rs_fp64_peak_three_operand(rs_ctx *ctx, double *tflops);   /* same loop, three distinct register operands per FMA (register-file bound) */
 int rs_set_tuning(rs_ctx *ctx, int br_variant);    /* blind-rotate kernel: 0 = warp-specialised (default); 1 / 2 = single-role, 7- / 4-stage BSK ring; 3 / 4 = warp-specialised with the BSK served from tensor memory (experimental) */
-int rs_set_ks_variant(rs_ctx *ctx, int ks_variant);   /* keyswitch kernel: 0 = smem-tiled, TMA-streamed KSK (default), 1 = un-tiled L1/L2 gather */
+int rs_set_ks_variant(rs_ctx *ctx, int ks_variant);   /* keyswitch kernel: 0 = auto (default: exact int8 GEMM on the tensor cores, tcgen05.mma kind::i8, for batches >= 2048; shared-memory gather with a TMA-streamed key below), 1 = un-tiled L1/L2 gather, 2 = tensor cores always, 3 = shared-memory gather always */
 int rs_device_info(rs_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
 
 #ifdef __cplusplus

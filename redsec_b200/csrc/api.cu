@@ -18,6 +18,7 @@
 #include "blind_rotate_ws.cuh"
 #include "blind_rotate_tm.cuh"
 #include "lwe_kernels.cuh"
+#include "keyswitch_mma.cuh"
 #include "params.h"
 
 namespace {
@@ -52,6 +53,10 @@ struct rs_ctx {
     uint32_t* ksk = nullptr;      // [N][t][base][LWE_STRIDE]  (un-tiled keyswitch, variant 1)
     uint32_t* ksk7 = nullptr;     // [N][t][7][LWE_STRIDE]     (tiled keyswitch, default)
     bool key_loaded = false;
+    // tensor-core keyswitch (variant 2): pre-tiled u8 key, transposed a' scratch
+    uint8_t* kskb = nullptr;
+    uint32_t* abar_t = nullptr; size_t abar_cap = 0;
+    uint32_t* bprime = nullptr; size_t bprime_cap = 0;
     // scratch (grow-only; no allocation on the steady-state hot path)
     uint32_t* ext = nullptr; size_t ext_cap = 0;        // extracted samples
     uint32_t* lin = nullptr; size_t lin_cap = 0;        // gate pre-combination
@@ -70,7 +75,8 @@ struct rs_ctx {
     uint64_t prof_n[RS_K_COUNT] = {0, 0, 0, 0};
     uint64_t launches = 0;
     int br_variant = 0;
-    int ks_variant = 0;
+    int ks_variant = 0;           // 0 auto (tensor cores for large batches, shared-memory gather below), 1 un-tiled gather, 2 tensor cores, 3 gather
+    int ks_mma_min = 2048;        // RS_KS_MMA_MIN: smallest batch the auto mode sends to the tensor cores
     int ws_split = 2;             // largest row-split factor of the warp-specialised kernel for batches below 2 ciphertexts per SM
                                   // (RS_WS_SPLIT=1 disables, =4 also spreads <= sm_count ciphertexts over 4 slots: measured 4.15 ms
                                   // against 3.90 ms for 2 slots, because four concurrent rows leave one BSK ring stage for look-ahead)
@@ -262,7 +268,30 @@ void ks_tiled_launch(rs_ctx* ctx, uint32_t* out, const uint32_t* ext, int count)
 int launch_keyswitch(rs_ctx* ctx, uint32_t* out, const uint32_t* ext, size_t count) {
     if (!ctx->key_loaded) return fail(ctx, RS_ERR_STATE, "rs_load_eval_key has not been called");
     if (count == 0) return RS_OK;
-    if (ctx->ks_variant == 1) {
+    // variant 0 (default) chooses by batch size: the tensor-core GEMM needs 256 ciphertexts x 64 words per CTA to fill the machine
+    // (2^16: 5.3 ms against 24.9 ms for the gather kernel), the shared-memory gather kernel splits the sum over the 1024
+    // coefficients across CTAs and wins on small batches (592: 0.27 ms against 0.5 ms)
+    const bool use_mma = ctx->ks_variant == 2 || (ctx->ks_variant == 0 && count >= (size_t)ctx->ks_mma_min);
+    if (use_mma) {
+        // exact int8 GEMM on the tensor cores (keyswitch_mma.cuh): tiled key built on first use from the padded table
+        if (!ctx->kskb) {
+            RS_CUDA(ctx, cudaMalloc(&ctx->kskb, rs::KSKB_BYTES));
+            LaunchScope ls(ctx, RS_K_OTHER);
+            rs::kskb_build_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->ksk, ctx->kskb);
+        }
+        const int stride = (int)((count + rs::KM_CTS - 1) / rs::KM_CTS) * rs::KM_CTS;
+        if (int r = grow(ctx, &ctx->abar_t, &ctx->abar_cap, (size_t)rs::N * stride)) return r;
+        if (int r = grow(ctx, &ctx->bprime, &ctx->bprime_cap, (size_t)stride)) return r;
+        {
+            LaunchScope ls(ctx, RS_K_KEYSWITCH);
+            dim3 grid((unsigned)(stride / 32), rs::N / 32), block(32, 8);
+            rs::ks_mma_prep_kernel<<<grid, block, 0, ctx->stream>>>(ext, (int)count, stride, ctx->abar_t, ctx->bprime);
+        }
+        RS_CUDA(ctx, cudaGetLastError());
+        LaunchScope ls(ctx, RS_K_KEYSWITCH);
+        dim3 grid((unsigned)(stride / rs::KM_CTS), rs::KM_NT);
+        rs::keyswitch_mma_kernel<<<grid, 320, rs::KmSmem::kTotal, ctx->stream>>>(ctx->abar_t, ctx->bprime, (int)count, stride, ctx->kskb, out);
+    } else if (ctx->ks_variant == 1) {
         const int grid = (int)((count + kKsTile - 1) / kKsTile);
         LaunchScope ls(ctx, RS_K_KEYSWITCH);
         rs::keyswitch_kernel<kKsTile><<<grid, rs::LWE_STRIDE, 0, ctx->stream>>>(ext, (int)count, ctx->ksk, out);
@@ -358,6 +387,7 @@ int rs_ctx_create(rs_ctx** out, int device) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rs::keyswitch_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::KsSmem<64>::kTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rs::keyswitch_tiled_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::KsSmem<32>::kTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rs::keyswitch_tiled_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::KsSmem<16>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rs::keyswitch_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rs::KmSmem::kTotal);
     if (e == cudaSuccess) e = br_prepare<4, 7>();
     if (e == cudaSuccess) e = br_prepare<4, 4>();
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
@@ -367,7 +397,8 @@ int rs_ctx_create(rs_ctx** out, int device) {
     if (const char* env = getenv("RS_WS_SPLIT")) { const int v = atoi(env); ctx->ws_split = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
     if (ctx->l2_keep > 0.f)   // the evict_last hint only holds lines inside the persisting carve-out (82.9 MB max on B200); best effort
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
-    if (const char* env = getenv("RS_KS_VARIANT")) { int v = atoi(env); if (v == 0 || v == 1) ctx->ks_variant = v; }
+    if (const char* env = getenv("RS_KS_VARIANT")) { int v = atoi(env); if (v >= 0 && v <= 3) ctx->ks_variant = v; }
+    if (const char* env = getenv("RS_KS_MMA_MIN")) { int v = atoi(env); if (v >= 1) ctx->ks_mma_min = v; }
     if (const char* env = getenv("RS_BR_VARIANT")) { int v = atoi(env); if (v >= 0 && v <= 4) ctx->br_variant = v; }
     *out = ctx;
     return RS_OK;
@@ -453,7 +484,7 @@ int rs_ctx_destroy(rs_ctx* ctx) {
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
     cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->ksk7); cudaFree(ctx->ext); cudaFree(ctx->lin); cudaFree(ctx->wire);
-    cudaFree(ctx->io0); cudaFree(ctx->io1);
+    cudaFree(ctx->io0); cudaFree(ctx->io1); cudaFree(ctx->kskb); cudaFree(ctx->abar_t); cudaFree(ctx->bprime);
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -935,7 +966,7 @@ int rs_debug_stats(unsigned long long* out8, int reset) {
 #endif
 
 int rs_set_ks_variant(rs_ctx* ctx, int ks_variant) {
-    if (!ctx || ks_variant < 0 || ks_variant > 1) return fail(ctx, RS_ERR_ARG, "rs_set_ks_variant: 0 (tiled) or 1 (un-tiled)");
+    if (!ctx || ks_variant < 0 || ks_variant > 3) return fail(ctx, RS_ERR_ARG, "rs_set_ks_variant: 0 (auto), 1 (un-tiled gather), 2 (tensor cores) or 3 (shared-memory gather)");
     ctx->ks_variant = ks_variant;
     return RS_OK;
 }

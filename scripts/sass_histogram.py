@@ -7,7 +7,8 @@ KEYS = ["UBLKCP", "UTMALDG", "SYNCS", "USETMAXREG", "DFMA", "DADD", "DMUL", "DMM
         "SHFL", "BAR", "MEMBAR", "UTCCP", "LDTM", "UTCBAR", "UTCHMMA", "UTCIMMA", "UTCQMMA", "UTCATOMSWS", "TCGEN"]
 WANT = [("blind_rotate_ws_kernelILi5ELi3ELi1ELb0", "blind_rotate_ws_kernel<5,3,1> (default, full waves)"),
         ("blind_rotate_ws_kernelILi5ELi3ELi2ELb0", "blind_rotate_ws_kernel<5,3,2> (row-split, <= 2 ciphertexts per SM)"),
-        ("keyswitch_tiled_kernelILi64", "keyswitch_tiled_kernel<64>"),
+        ("keyswitch_mma_kernel", "keyswitch_mma_kernel (default keyswitch for batches >= 2048: tcgen05.mma kind::i8 = UTCIMMA, accumulators in TMEM, LDTM epilogue)"),
+        ("keyswitch_tiled_kernelILi64", "keyswitch_tiled_kernel<64> (shared-memory gather keyswitch, small batches)"),
         ("lwe_conv_kernelILb0", "lwe_conv_kernel<false>"),
         ("lwe_lincomb_kernel", "lwe_lincomb_kernel"),
         ("bsk_to_fourier_kernel", "bsk_to_fourier_kernel (key conversion)"),
@@ -36,7 +37,7 @@ for key, title in WANT:
             reuse = sum(1 for ins in body if ins.split()[0].startswith("DFMA") and ".reuse" in ins)
             out.append(f"== {title}\n   mangled: {name}\n   {len(body)} instructions; " + ", ".join(f"{k} {c[k]}" for k in KEYS if c[k]) +
                        f"; DFMA with a .reuse operand {reuse}")
-            samples = [ins for ins in body if any(ins.split()[0].startswith(k) for k in ("UBLKCP", "USETMAXREG", "UTCCP", "LDTM"))][:4]
+            samples = [ins for ins in body if any(ins.split()[0].startswith(k) for k in ("UBLKCP", "USETMAXREG", "UTCCP", "LDTM", "UTCIMMA", "UTCBAR"))][:5]
             for s_ in samples:
                 out.append("      " + s_)
             out.append("")

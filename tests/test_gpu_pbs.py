@@ -28,30 +28,37 @@ def test_blind_rotate_extract_bit_exact(oracle, keyset, engine):
         assert np.array_equal(ext_gpu[c], O.sample_extract(acc)), f"ciphertext {c}"
 
 
-@pytest.mark.parametrize("count", [9, 1500])
-def test_keyswitch_bit_exact(oracle, keyset, engine, count):
-    """smem-tiled keyswitch (TILE 16 / 32 paths, split-sum with red.add) against the oracle on random extracted samples."""
+@pytest.mark.parametrize("variant", [3, 2], ids=["smem-gather", "tensor-cores"])
+@pytest.mark.parametrize("count", [9, 257, 1500])
+def test_keyswitch_bit_exact(oracle, keyset, engine, count, variant):
+    """Both keyswitch kernels against the oracle on random extracted samples: the shared-memory gather kernel (TILE 16 / 32 paths,
+    split sum with atomics) and the exact int8 GEMM on the tensor cores (tcgen05.mma kind::i8; ragged last M tile)."""
     rng = np.random.default_rng(5 + count)
     ext = rng.integers(0, 2 ** 32, size=(count, 1025), dtype=np.uint64).astype(np.uint32)
     ext[0, :1024] = 0                       # all digits 0: only (0, b) survives
     ext[1, :1024] = 0xFFFFFFFF              # carries through every digit
-    got = engine.keyswitch(ext)
+    engine.set_ks_variant(variant)
+    try:
+        got = engine.keyswitch(ext)
+    finally:
+        engine.set_ks_variant(0)
     want = oracle.keyswitch(ext, keyset)
     assert np.array_equal(got, want)
 
 
-def test_keyswitch_tiled_matches_untiled_at_scale(engine, keyset):
-    """TILE 64 path with a ragged last tile: 20 001 ciphertexts, tiled kernel vs the un-tiled gather kernel (both bit-exact
-    vs the oracle on the small cases above; integer sums, so any difference is a bug)."""
+def test_keyswitch_variants_agree_at_scale(engine, keyset):
+    """20 001 ciphertexts (ragged last tile in every kernel): the default (auto: tensor cores at this size), the shared-memory
+    gather kernel (TILE 64 path) and the un-tiled gather kernel give the same words (all three are bit-exact vs the oracle on
+    the small cases above; integer sums, so any difference is a bug)."""
     rng = np.random.default_rng(9)
     ext = rng.integers(0, 2 ** 32, size=(20001, 1025), dtype=np.uint64).astype(np.uint32)
     got = engine.keyswitch(ext)
-    engine.set_ks_variant(1)
     try:
-        want = engine.keyswitch(ext)
+        for v in (1, 3):
+            engine.set_ks_variant(v)
+            assert np.array_equal(engine.keyswitch(ext), got), f"keyswitch variant {v}"
     finally:
         engine.set_ks_variant(0)
-    assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("count", [1, 5, 6, 7, 200, 300])
