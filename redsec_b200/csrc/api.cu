@@ -81,6 +81,8 @@ struct rs_ctx {
                                   // (RS_WS_SPLIT=1 disables, =4 also spreads <= sm_count ciphertexts over 4 slots: measured 4.15 ms
                                   // against 3.90 ms for 2 slots, because four concurrent rows leave one BSK ring stage for look-ahead)
     float l2_keep = 0.45f;        // fraction of the BSK stream hinted L2 evict_last (RS_L2_KEEP; measured optimum)
+    bool ws_producer = true;      // 16-warp build of the warp-specialised kernel with a dedicated BSK producer warp; RS_WS_PRODUCER=0: the 12-warp
+                                  // build whose front warps claim the slabs (A/B knob)
     bool ws_stress = false;       // RS_WS_STRESS=1: row-split launches use the instantiation that delays one back-warp pair (tests)
     std::vector<Lane> lanes;      // parked state of the lanes that are not selected (stream / ext / lin below belong to lane `cur_lane`)
     int cur_lane = 0;
@@ -230,18 +232,25 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
                 in, (int)count, mu, ctx->bsk_f, ext);
         else if (ctx->br_variant == 4)
             rs::blind_rotate_tm_kernel<4, 3, 120, 184><<<grid, 512, rs::TmSmem<5, 3>::kTotal, ctx->stream>>>(in, (int)count, mu, ctx->bsk_f, ext);
-        else if (ctx->br_variant == 0 && split == 4)
-            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 4><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
-                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);
-        else if (ctx->br_variant == 0 && split == 2 && ctx->ws_stress)
-            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2, true><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
-                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);
-        else if (ctx->br_variant == 0 && split == 2)
-            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
-                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);
-        else if (ctx->br_variant == 0)
-            rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 1><<<bgrid, 384, rs::WsSmem<kWsStages, kWsSlots>::kTotal, ctx->stream>>>(
-                in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);
+        else if (ctx->br_variant == 0) {
+            // warp-specialised kernel: 16-warp build with a BSK producer warp (default), or the 12-warp build whose front warps
+            // claim the slabs themselves (RS_WS_PRODUCER=0, the round-1 shape, kept for A/B runs)
+            const int smem = rs::WsSmem<kWsStages, kWsSlots>::kTotal;
+#define RS_WS_LAUNCH(SPLIT_, STRESS_)                                                                                              \
+            do {                                                                                                                   \
+                if (ctx->ws_producer)                                                                                              \
+                    rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, SPLIT_, STRESS_, true><<<bgrid, 512, smem, ctx->stream>>>(     \
+                        in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);                                          \
+                else                                                                                                               \
+                    rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, SPLIT_, STRESS_, false><<<bgrid, 384, smem, ctx->stream>>>(    \
+                        in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);                                          \
+            } while (0)
+            if (split == 4) RS_WS_LAUNCH(4, false);
+            else if (split == 2 && ctx->ws_stress) RS_WS_LAUNCH(2, true);
+            else if (split == 2) RS_WS_LAUNCH(2, false);
+            else RS_WS_LAUNCH(1, false);
+#undef RS_WS_LAUNCH
+        }
         else if (ctx->br_variant == 1) br_launch<4, 7>(ctx, grid, in, (int)count, mu, ext, lut, lut_mod);
         else br_launch<4, 4>(ctx, grid, in, (int)count, mu, ext, lut, lut_mod);
     }
@@ -368,17 +377,19 @@ int rs_ctx_create(rs_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             rs::WsSmem<kWsStages, kWsSlots>::kTotal);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 rs::WsSmem<kWsStages, kWsSlots>::kTotal);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 rs::WsSmem<kWsStages, kWsSlots>::kTotal);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             rs::WsSmem<kWsStages, kWsSlots>::kTotal);
+    e = cudaSuccess;
+    {
+        const int smem = rs::WsSmem<kWsStages, kWsSlots>::kTotal;
+        auto opt_in = [&](auto kernel) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); };
+        opt_in(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 1, false, true>);
+        opt_in(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2, false, true>);
+        opt_in(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2, true, true>);
+        opt_in(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 4, false, true>);
+        opt_in(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 1, false, false>);
+        opt_in(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2, false, false>);
+        opt_in(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 2, true, false>);
+        opt_in(rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, 4, false, false>);
+    }
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(rs::blind_rotate_tm_kernel<5, 3, 120, 184>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  rs::TmSmem<5, 3>::kTotal);
@@ -394,6 +405,7 @@ int rs_ctx_create(rs_ctx** out, int device) {
     if (const char* env = getenv("RS_L2_KEEP")) { float v = (float)atof(env); if (v >= 0.f && v <= 1.f) ctx->l2_keep = v; }
     if (const char* env = getenv("RS_POOL_CAP_MB")) ctx->pool_cap_bytes = (size_t)atoll(env) << 20;
     if (const char* env = getenv("RS_WS_STRESS")) ctx->ws_stress = atoi(env) != 0;
+    if (const char* env = getenv("RS_WS_PRODUCER")) ctx->ws_producer = atoi(env) != 0;
     if (const char* env = getenv("RS_WS_SPLIT")) { const int v = atoi(env); ctx->ws_split = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
     if (ctx->l2_keep > 0.f)   // the evict_last hint only holds lines inside the persisting carve-out (82.9 MB max on B200); best effort
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);

@@ -94,8 +94,8 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 template <int N_REGS>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N_REGS)); }
 
-template <int STAGES, int XSLOTS, int SPLIT, bool STRESS = false>
-__global__ void __launch_bounds__(384, 1)
+template <int STAGES, int XSLOTS, int SPLIT, bool STRESS = false, bool PRODUCER = false>
+__global__ void __launch_bounds__(PRODUCER ? 512 : 384, 1)
 blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_STRIDE]
                        int count, uint32_t mu,
                        const double2* __restrict__ bsk_f,       // [n][BK_ROWS][2][NH]
@@ -142,6 +142,30 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     }
     __syncthreads();
 
+    if (PRODUCER && warp >= 12) {
+        // =========================================================================================== PRODUCER warpgroup (16-warp build)
+        // One lane of warp 12 streams the BSK slabs in order through the ring: no claim, no shared counter, and the front warps
+        // lose their producer duty.  setmaxnreg is a warpgroup instruction, so the build launches a whole fourth warpgroup (warps
+        // 13-15 leave at once).  Register pool: 512 x 128 = 65 536 = 8 x 32 x 184 (back) + 4 x 32 x 120 (front) + 4 x 32 x 24.
+        reg_dealloc<24>();
+        if (warp == 12 && lane == 0) {
+            const uint8_t* bsk_bytes = reinterpret_cast<const uint8_t*>(bsk_f);
+            const uint64_t l2pol = l2_policy_evict_last(l2_keep);
+#pragma unroll 1
+            for (int cur = 0; cur < kTotalRows; cur++) {
+                const int ns = cur % STAGES;
+                if (cur >= STAGES) mbar_wait_thread(bar_base + (S::kBskEmpty + ns) * 8, ((cur - STAGES) / STAGES) & 1);
+                mbar_arrive_expect_tx(bar_base + (S::kBskFull + ns) * 8, S::kStageBytes);
+                if (l2_keep > 0.f)
+                    tma_load_1d_hint(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
+                                     S::kStageBytes, bar_base + (S::kBskFull + ns) * 8, l2pol);
+                else
+                    tma_load_1d(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
+                                S::kStageBytes, bar_base + (S::kBskFull + ns) * 8);
+            }
+        }
+        return;
+    }
     if (warp >= 8) {
         // =========================================================================================== FRONT warp
         reg_dealloc<120>();
@@ -180,6 +204,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         // after the row has been handed to the back warps: the claim is a chain of shared-memory round trips (counter, CAS, stage
         // barrier, expect_tx, bulk copy) of ~700 cycles that would otherwise delay every row by as much
         auto request_slabs = [&](int upto) {
+            if (PRODUCER) return;      // the 13-warp build has a warp for this
             if (lane == 0) {
                 const int want = min(upto, kTotalRows - 1);
                 int cur = *reinterpret_cast<volatile int*>(issued);
@@ -289,7 +314,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     }
 
     // =============================================================================================== BACK warp
-    reg_alloc<192>();
+    reg_alloc<PRODUCER ? 184 : 192>();
     const int j = warp >> 1;               // slot
     const int jc = j / SPLIT;
     const int part = j % SPLIT;
