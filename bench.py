@@ -340,8 +340,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "note": "a DFMA with three distinct register operands issues every 3 cycles instead of 2 (register-file bound, scripts/probes/fp64_probe2.cu); "
                                  "peak_three_register_fma is that rate measured live, the ceiling of the MAC and twiddle FMAs",
                          "traffic_source": "static: read from profiles/r2_traffic.json, one ncu capture of a 2^16-ciphertext launch (a bench run is never profiled)",
-                         "traffic_note": "DRAM bytes of one 2^16-ciphertext blind-rotate launch; the Fourier BSK (114.7 MB) is re-streamed from DRAM about twice per wave "
-                                         "of CTAs; the algorithmic bytes count it once; HBM use stays below 1 % of peak either way",
+                         "traffic_note": "DRAM bytes of one 2^16-ciphertext blind-rotate launch; varies 70-220 GB between boxes: the CTAs of a wave finish ~1 % apart, the next wave's CTAs "
+                                         "then walk the 114.7 MB Fourier key out of step and re-read it from DRAM (L2 hit rate 75-90 %). RS_WS_GATE=1 re-aligns every wave: 6.8 GB, "
+                                         "99 % hit rate, 1.2 % slower (profiles/r2_traffic_ab.txt) -- the kernel is FP64-bound and HBM at most 4 % busy, so the gate is off",
                          "hbm": {"algorithmic_bytes_per_launch": BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4),
                                  "achieved_gbs": (BSK_FOURIER_BYTES + G * (352 * 4 + 1028 * 4)) / br_avg_s / 1e9,
                                  "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

@@ -77,10 +77,15 @@ struct rs_ctx {
     int br_variant = 0;
     int ks_variant = 0;           // 0 auto (tensor cores for large batches, shared-memory gather below), 1 un-tiled gather, 2 tensor cores, 3 gather
     int ks_mma_min = 2048;        // RS_KS_MMA_MIN: smallest batch the auto mode sends to the tensor cores
-    int ws_split = 2;             // largest row-split factor of the warp-specialised kernel for batches below 2 ciphertexts per SM
-                                  // (RS_WS_SPLIT=1 disables, =4 also spreads <= sm_count ciphertexts over 4 slots: measured 4.15 ms
-                                  // against 3.90 ms for 2 slots, because four concurrent rows leave one BSK ring stage for look-ahead)
+    int ws_split = 4;             // largest row-split factor of the warp-specialised kernel for batches below 2 ciphertexts per SM:
+                                  // <= sm_count ciphertexts are spread over 4 slots of a CTA each, <= 2 sm_count over 2 (RS_WS_SPLIT=1
+                                  // disables, =2 caps at 2).  With the producer warp 4 slots beat 2 (3.00 against 3.35 ms per launch);
+                                  // with the round-1 claim protocol they lost (4.15 against 3.90 ms: four front warps claiming slabs)
     float l2_keep = 0.45f;        // fraction of the BSK stream hinted L2 evict_last (RS_L2_KEEP; measured optimum)
+    int ws_gate = 0;              // RS_WS_GATE=n: CTAs of every n-th wave of a long un-split launch wait for the earlier waves (0 = off, the default:
+                                  // n = 1 cuts the launch's DRAM reads from 70-220 GB to 7 GB and costs 1.2 % of time; HBM is 4 % busy either way)
+    unsigned* wave_done = nullptr;   // [16] one gate counter per lane
+    int ws_lookahead = 5;         // RS_WS_LOOKAHEAD (1..5): BSK slabs the producer warp requests ahead of the slowest consumer
     bool ws_producer = true;      // 16-warp build of the warp-specialised kernel with a dedicated BSK producer warp; RS_WS_PRODUCER=0: the 12-warp
                                   // build whose front warps claim the slabs (A/B knob)
     bool ws_stress = false;       // RS_WS_STRESS=1: row-split launches use the instantiation that delays one back-warp pair (tests)
@@ -236,14 +241,20 @@ int launch_blind_rotate(rs_ctx* ctx, uint32_t* ext, const uint32_t* in, size_t c
             // warp-specialised kernel: 16-warp build with a BSK producer warp (default), or the 12-warp build whose front warps
             // claim the slabs themselves (RS_WS_PRODUCER=0, the round-1 shape, kept for A/B runs)
             const int smem = rs::WsSmem<kWsStages, kWsSlots>::kTotal;
+            // wave gate of long un-split launches (blind_rotate_ws.cuh): one counter per lane, cleared on the launch stream
+            unsigned* gate = nullptr;
+            if (ctx->ws_producer && ctx->ws_gate > 0 && split == 1 && (size_t)bgrid > (size_t)ctx->ws_gate * sms && ctx->wave_done) {
+                gate = ctx->wave_done + ctx->cur_lane;
+                RS_CUDA(ctx, cudaMemsetAsync(gate, 0, sizeof(unsigned), ctx->stream));
+            }
 #define RS_WS_LAUNCH(SPLIT_, STRESS_)                                                                                              \
             do {                                                                                                                   \
                 if (ctx->ws_producer)                                                                                              \
                     rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, SPLIT_, STRESS_, true><<<bgrid, 512, smem, ctx->stream>>>(     \
-                        in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);                                          \
+                        in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod, ctx->ws_lookahead, gate, (int)sms, ctx->ws_gate); \
                 else                                                                                                               \
                     rs::blind_rotate_ws_kernel<kWsStages, kWsSlots, SPLIT_, STRESS_, false><<<bgrid, 384, smem, ctx->stream>>>(    \
-                        in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod);                                          \
+                        in, (int)count, mu, ctx->bsk_f, ext, ctx->l2_keep, lut, lut_mod, ctx->ws_lookahead, gate, (int)sms, ctx->ws_gate); \
             } while (0)
             if (split == 4) RS_WS_LAUNCH(4, false);
             else if (split == 2 && ctx->ws_stress) RS_WS_LAUNCH(2, true);
@@ -406,6 +417,8 @@ int rs_ctx_create(rs_ctx** out, int device) {
     if (const char* env = getenv("RS_POOL_CAP_MB")) ctx->pool_cap_bytes = (size_t)atoll(env) << 20;
     if (const char* env = getenv("RS_WS_STRESS")) ctx->ws_stress = atoi(env) != 0;
     if (const char* env = getenv("RS_WS_PRODUCER")) ctx->ws_producer = atoi(env) != 0;
+    if (const char* env = getenv("RS_WS_GATE")) ctx->ws_gate = std::max(atoi(env), 0);
+    if (const char* env = getenv("RS_WS_LOOKAHEAD")) ctx->ws_lookahead = std::min(std::max(atoi(env), 1), kWsStages);
     if (const char* env = getenv("RS_WS_SPLIT")) { const int v = atoi(env); ctx->ws_split = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
     if (ctx->l2_keep > 0.f)   // the evict_last hint only holds lines inside the persisting carve-out (82.9 MB max on B200); best effort
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
@@ -496,7 +509,7 @@ int rs_ctx_destroy(rs_ctx* ctx) {
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.start); cudaEventDestroy(ev.stop); }
     cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->ksk7); cudaFree(ctx->ext); cudaFree(ctx->lin); cudaFree(ctx->wire);
-    cudaFree(ctx->io0); cudaFree(ctx->io1); cudaFree(ctx->kskb); cudaFree(ctx->abar_t); cudaFree(ctx->bprime);
+    cudaFree(ctx->io0); cudaFree(ctx->io1); cudaFree(ctx->kskb); cudaFree(ctx->abar_t); cudaFree(ctx->bprime); cudaFree(ctx->wave_done);
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -538,6 +551,7 @@ int rs_load_eval_key(rs_ctx* ctx, const uint32_t* bsk_host, const uint32_t* ksk_
     if (!ctx->bsk_f) RS_CUDA(ctx, cudaMalloc(&ctx->bsk_f, rs::BSK_F_BYTES));
     if (!ctx->ksk) RS_CUDA(ctx, cudaMalloc(&ctx->ksk, rs::KSK_DEV_WORDS * sizeof(uint32_t)));
     if (!ctx->ksk7) RS_CUDA(ctx, cudaMalloc(&ctx->ksk7, rs::KSK_TILED_WORDS * sizeof(uint32_t)));
+    if (!ctx->wave_done) RS_CUDA(ctx, cudaMalloc(&ctx->wave_done, 16 * sizeof(unsigned)));
     // staging for the torus32 keys (freed after conversion)
     uint32_t* stage = nullptr;
     const size_t ksk_bytes = RS_KSK_WORDS * sizeof(uint32_t), bsk_bytes = RS_BSK_WORDS * sizeof(uint32_t);
@@ -954,6 +968,12 @@ int rs_debug_err_stats(unsigned long long* hist8, double* max_err) {   // debug 
 int rs_debug_ws_prof(long long* out96) {   // debug builds only: phase timers of CTA 0, [12 warps][8 phases]
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(out96, rs::g_ws_prof, sizeof(long long) * 96) == cudaSuccess ? 0 : 1;
+}
+int rs_debug_ws_rowwait(long long* out60) {   // [3][20], see blind_rotate_ws.cuh
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out60, rs::g_ws_rowwait, sizeof(long long) * 60) != cudaSuccess) return 1;
+    static const long long zero[60] = {0};
+    return cudaMemcpyToSymbol(rs::g_ws_rowwait, zero, sizeof(zero)) == cudaSuccess ? 0 : 1;   // read and reset
 }
 #endif
 

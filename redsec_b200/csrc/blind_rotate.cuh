@@ -10,9 +10,10 @@
 // so each BSK byte is fetched once per CTA per step and reused GROUPS times.  There is no fixed producer: the first
 // group to start row rc claims (CAS on a shared counter) and requests every slab up to rc+AHEAD, so the group that
 // runs ahead feeds the ring, followers find their slabs already resident, and the leader is throttled only by the
-// ring depth.  (A fixed producer thread paces the CTA: measured, the other three groups spent 27 % of their time
-// waiting for slabs it had not requested yet.  A dedicated producer warp would be the 4k+1-th warp of the CTA and
-// push one SM sub-partition to an extra resident warp, which cuts the register budget of every thread.)
+// ring depth.  (A fixed producer THREAD inside one of the groups paces the CTA: measured, the other three groups spent 27 % of
+// their time waiting for slabs it had not requested yet.  The warp-specialised kernel, blind_rotate_ws.cuh, gives the job to a
+// warpgroup of its own instead -- a thread that does nothing else never lags -- and pays for it with 8 registers per back-warp
+// thread; that is the default path.  This kernel is variant 1 / 2 of rs_set_tuning.)
 #pragma once
 #include "fft512.cuh"
 #include "params.h"

@@ -4,15 +4,17 @@
 // redcufhe::Bootstrap at lib/GPU/gates.cu:124-130 for a whole batch), re-cut as a three-stage pipeline so that every SM
 // sub-partition has THREE resident warps with different phases instead of two in near lock-step:
 //
-//   TMA (cp.async.bulk)  --BSK ring-->  BACK warps  <--exchange ring--  FRONT warps
+//   PRODUCER warp: TMA (cp.async.bulk)  --BSK ring-->  BACK warps  <--exchange ring--  FRONT warps
 //
-// One CTA = 12 warps = 3 warpgroups, 4 ciphertexts:
+// One CTA = 4 warpgroups, 4 ciphertexts (the default, PRODUCER = true; 512 threads):
+//   * warpgroup 3 = the BSK producer: one lane of warp 12 streams the 16 KiB Fourier-key slabs in order through the STAGES-deep
+//     ring (wait bsk_empty of the stage's previous occupant, expect_tx, cp.async.bulk).  setmaxnreg is a warpgroup instruction,
+//     so a whole warpgroup is launched for it; warps 13-15 shrink to 24 registers and leave.
 //   * warpgroup 2 = 4 FRONT warps, one per ciphertext.  A front warp owns the torus32 accumulator (shared memory): per
 //     blind-rotate step it forms (X^a - 1)*acc, gadget-decomposes it, and for each of the 20 (polynomial, level) rows
 //     runs pass 1 of the forward transform (twist + radix-8) for all 64 thread-columns (two halves of 32) and writes the
-//     result into a 3-slot exchange ring.  After handing a row over it claims and requests BSK slabs (TMA) -- at the END of
-//     the row, because the claim is ~700 cycles of dependent shared-memory round trips that must not delay the hand-over.
-//     It is the lighter role on purpose: the ring stays full and the back warps, which carry the FP64 bulk, rarely wait.
+//     result into a 3-slot exchange ring.  It is the lighter role on purpose: the ring stays full and the back warps, which
+//     carry the FP64 bulk, rarely wait (measured: only at the first row of a step, profiles/r2_ws_phase_timers.txt).
 //   * warpgroups 0,1 = 8 BACK warps, two per ciphertext.  A back warp reads a row from the exchange ring, runs passes 2
 //     and 3 (twiddles fused as FMAs, exchange 2 through shuffles), multiplies by the BSK slab and accumulates in
 //     registers (Fourier accumulators, 64 registers).  After 20 rows the pair runs both inverse transforms (their
@@ -20,9 +22,15 @@
 //     accumulator and signals acc_ready per polynomial, polynomial 0 first, so the front warp restarts early.
 //   The two back warps of a ciphertext never synchronise with each other during the 20 rows (exchange 1 is now
 //   front -> back, exchange 2 is intra-warp); all hand-offs are mbarriers, so the roles drift freely within the rings.
-//   * Registers are redistributed with setmaxnreg: launch at 168/thread (12 warps), front warps drop to 120, back warps
-//     grow to 192.  The pool is what the launch allocated (384*168 = 64512 registers, not the 65536 of the SM):
-//     8*32*192 + 4*32*120 = 64512.  (Asking for more blocks setmaxnreg.inc forever.)
+//   * Registers are redistributed with setmaxnreg: launch at 128/thread (16 warps = the whole file), producer warpgroup
+//     drops to 24, front warps to 120, back warps grow to 184: 8*32*184 + 4*32*120 + 4*32*24 = 65536.
+//
+// PRODUCER = false is the round-1 shape (12 warps, launch at 168, back 192 / front 120), kept behind RS_WS_PRODUCER=0 for A/B
+// runs: there is no producer warp and the front warps request the slabs, in order, through a shared claim counter at the end of
+// each of their rows.  That duty cost a front warp ~520 of its ~2200 cycles per row and made it the critical path of a lone
+// ciphertext; the producer warpgroup costs the back warps 8 registers and nothing else.  Measured, same inputs, bit-identical
+// outputs (profiles/r2_ws_producer_ab.log): 2^16 bootstraps 842 -> 791 ms, one wave of 592 7.75 -> 7.18 ms, a single
+// ciphertext 3.79 -> 3.33 ms.
 //
 // Row-split mode (SPLIT = 2; 4 exists but is slower, see api.cu) for batches below two ciphertexts per SM, which are
 // latency-bound (a ciphertext alone on an SM needs 6.1 ms un-split: 7 000 rows one after the other): the 4 slots of a CTA
@@ -44,6 +52,11 @@ namespace rs {
 // per-warp phase timers of CTA 0 (debug builds only: RS_NVCC_EXTRA=-DRS_WS_PROF, read with scripts/ws_prof.py):
 // [warp][phase] accumulated clock64 cycles.  Results: profiles/r1_ws_phase_timers.txt
 __device__ long long g_ws_prof[12][8];
+// where in a step the hand-off waits fall (warp 0 = back, warp 8 = front, CTA 0): [0][row] back warp waiting for row `row` of a step,
+// [1][row] front warp waiting for a free ring slot before row `row`, [2][c] front warp waiting for accumulator polynomial c
+__device__ long long g_ws_rowwait[3][20];
+#define WSP_ROWWAIT_BEGIN long long wsp_rw = clock64()
+#define WSP_ROWWAIT_END(kind, idx) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8)) g_ws_rowwait[kind][idx] += clock64() - wsp_rw; } while (0)
 #define WSP_DECL long long wsp_t = clock64(), wsp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define WSP(phase) do { const long long n_ = clock64(); wsp_acc[phase] += n_ - wsp_t; wsp_t = n_; } while (0)
 #define WSP_FLUSH() do { if (blockIdx.x == 0 && lane == 0) for (int q_ = 0; q_ < 8; q_++) g_ws_prof[warp][q_] = wsp_acc[q_]; } while (0)
@@ -51,6 +64,8 @@ __device__ long long g_ws_prof[12][8];
 #define WSP_DECL
 #define WSP(phase) do { } while (0)
 #define WSP_FLUSH() do { } while (0)
+#define WSP_ROWWAIT_BEGIN do { } while (0)
+#define WSP_ROWWAIT_END(kind, idx) do { } while (0)
 #endif
 
 #ifdef RS_ERR_STATS
@@ -102,7 +117,10 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                        uint32_t* __restrict__ ext_out,          // [count][EXT_STRIDE]
                        float l2_keep,                           // fraction of the BSK stream marked L2 evict_last (0 = no hint)
                        const uint32_t* __restrict__ lut,        // [lut_mod][N] test vectors (ciphertext c uses row c % lut_mod), or
-                       int lut_mod)                             // nullptr: the constant test vector mu of the sign bootstrap
+                       int lut_mod,                             // nullptr: the constant test vector mu of the sign bootstrap
+                       int lookahead,                           // producer warp: slabs requested ahead of the slowest consumer (1..STAGES)
+                       unsigned* __restrict__ wave_done,        // wave gate (see below): ciphertexts finished so far in this launch, or nullptr
+                       int wave_ctas, int gate_every)           // CTAs per wave (= SMs), gate every gate_every-th wave
 {
     using S = WsSmem<STAGES, XSLOTS>;
     static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "a ciphertext is spread over 1, 2 or 4 slots");
@@ -123,6 +141,23 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // Wave gate (un-split launches of many waves; OFF by default, RS_WS_GATE=n).  All CTAs walk the 115 MB Fourier key from slab 0; as
+    // long as they do it together every slab leaves HBM once per wave and the other 147 CTAs find it in L2.  Nothing keeps them
+    // together: the producer warp hides a CTA's own L2 misses and SMs finish their CTAs ~1 % apart, which is enough to spread the
+    // CTAs of the next wave over more key than the L2 holds -- measured on 2^16-ciphertext launches: 73-220 GB of DRAM reads instead
+    // of 7 (profiles/r2_traffic_ab.txt).  With the gate the CTAs of every n-th wave start only when all ciphertexts of the earlier waves
+    // are finished (a counter the front warps bump), which lines the SMs up again: n = 1 restores 6.8 GB and a 99 % L2 hit rate and
+    // costs 1.2 % of time (every SM waits for the slowest); n = 4 already loses most of the effect.  The launch is FP64-bound and HBM is
+    // 4 % busy at worst, so time wins and the gate stays off.  The wait is bounded (200 us): a gate that cannot be met -- SMs shared
+    // with another kernel -- is skipped, never a hang.
+    if (SPLIT == 1 && wave_done != nullptr && threadIdx.x == 0) {
+        const int wave = blockIdx.x / wave_ctas;
+        if (wave > 0 && wave % gate_every == 0) {
+            const unsigned need = (unsigned)((long long)wave * wave_ctas * count / gridDim.x);
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile unsigned*>(wave_done) < need && clock64() - t0 < 400000LL) __nanosleep(100);
+        }
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(bar_base + (S::kBskFull + s) * 8, 1);
@@ -154,7 +189,12 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
 #pragma unroll 1
             for (int cur = 0; cur < kTotalRows; cur++) {
                 const int ns = cur % STAGES;
-                if (cur >= STAGES) mbar_wait_thread(bar_base + (S::kBskEmpty + ns) * 8, ((cur - STAGES) / STAGES) & 1);
+                // slab cur goes out once every consumer has released slab cur - lookahead.  lookahead = STAGES uses the whole ring;
+                // a shorter look-ahead leaves a CTA that runs ahead of the others exposed to its own L2 misses, which keeps the
+                // CTAs of a long launch walking the key together (BSK streaming).  The barrier of slab cur - lookahead
+                // cannot be a phase ahead of the one waited for: its stage's next occupant, cur - lookahead + STAGES, is not out yet.
+                const int rel = cur - (SPLIT == 1 ? lookahead : STAGES);      // the row-split modes work on SPLIT slabs at once: whole ring
+                if (rel >= 0) mbar_wait_thread(bar_base + (S::kBskEmpty + rel % STAGES) * 8, (rel / STAGES) & 1);
                 mbar_arrive_expect_tx(bar_base + (S::kBskFull + ns) * 8, S::kStageBytes);
                 if (l2_keep > 0.f)
                     tma_load_1d_hint(smem_base + S::kStagesOff + ns * S::kStageBytes, bsk_bytes + (size_t)cur * S::kStageBytes,
@@ -257,7 +297,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                 WSP(7);
                 // the back warps have added step i-1 into accumulator polynomial c.  Polynomial 0 is released first, so the rows of
                 // c = 0 are produced while the back warps still run the inverse transform of polynomial 1 (no bubble at the step boundary)
+                { WSP_ROWWAIT_BEGIN;
                 if (i > 0) mbar_wait_warp_long(accready + c * 8, (i - 1) & 1);
+                WSP_ROWWAIT_END(2, c); }
                 WSP(0);
                 uint32_t src[2][16];   // (X^a - 1)*acc_c + decomposition offset at this lane's 2 x 16 coefficients
 #pragma unroll
@@ -276,7 +318,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
                     WSP(2);
                     // ---- ring slot: wait until both back warps have read its previous occupant
                     const int slot = rowc % XSLOTS;
+                    { WSP_ROWWAIT_BEGIN;
                     if (rowc >= XSLOTS) mbar_wait_warp(xempty + slot * 8, ((rowc - XSLOTS) / XSLOTS) & 1);
+                    WSP_ROWWAIT_END(1, c * BK_L + p); }
                     WSP(3);
                     double2* buf = ring + slot * FFT_BUF;
                     const DigitLevel dl = digit_level(p);
@@ -310,6 +354,7 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
         for (int k = lane; k < N; k += 32) ext[k] = (k == 0) ? acc[0] : 0u - acc[N - k];
         if (lane == 0) { ext[N] = acc[N]; ext[N + 1] = 0; ext[N + 2] = 0; ext[N + 3] = 0; }
         __threadfence();      // the extracted sample is read by the keyswitch launch that follows (RS_END_FENCE, lwe_kernels.cuh)
+        if (SPLIT == 1 && wave_done != nullptr && lane == 0) atomicAdd(wave_done, 1u);
         return;
     }
 
@@ -350,7 +395,9 @@ blind_rotate_ws_kernel(const uint32_t* __restrict__ lwe_in,    // [count][LWE_ST
             const bool slab_ready = __all_sync(0xffffffffu, mbar_test(bar_base + (S::kBskFull + s) * 8, (slab / STAGES) & 1));
             // the row's exchange slot was tested before the previous row's MAC; only a miss pays the mbarrier round trip here
             WSP(7);
+            { WSP_ROWWAIT_BEGIN;
             if (!__all_sync(0xffffffffu, row_ready)) mbar_wait_warp_long(xfull + slot * 8, (rowc / XSLOTS) & 1);
+            WSP_ROWWAIT_END(0, row); }
             WSP(0);
             const double2* buf = ring + slot * FFT_BUF;
             double2 v[8];

@@ -15,5 +15,5 @@ dev = eng.upload(ct); out = eng.alloc(count)
 for _ in range(2):
     eng.pbs(dev, 0x20000000, out); eng.sync()
 PY
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_bytes.sum --clock-control none -k regex:"blind_rotate|keyswitch_tiled" -s 2 -c 2 --csv --log-file gpurun_out/traffic_${TAG}.csv python /tmp/traffic_run.py > gpurun_out/traffic_${TAG}.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_bytes.sum --clock-control none -k regex:"blind_rotate|keyswitch_mma|keyswitch_tiled" -s 2 -c 2 --csv --log-file gpurun_out/traffic_${TAG}.csv python /tmp/traffic_run.py > gpurun_out/traffic_${TAG}.log 2>&1
 tail -3 gpurun_out/traffic_${TAG}.log; cat gpurun_out/traffic_${TAG}.csv | tail -12

@@ -22,3 +22,10 @@ for count in [int(a) for a in sys.argv[1:]] or [148, 592]:
         tot = a[w].sum()
         if tot == 0: continue
         print(f" warp {w:2d} {'back ' if w < 8 else 'front'} total {tot/7000:7.0f}: " + ", ".join(f"{n} {a[w][k]/7000:6.0f}" for k, n in enumerate(names) if n != "-"))
+    rw = (C.c_longlong * 60)()
+    if hasattr(lib, "rs_debug_ws_rowwait"):
+        lib.rs_debug_ws_rowwait(rw)
+        r = np.array(rw[:]).reshape(3, 20) / 350.0
+        print("   back warp 0, cycles per step waiting for row r of the step :", " ".join(f"{x:5.0f}" for x in r[0]))
+        print("   front warp 8, cycles per step waiting for a free slot, row r:", " ".join(f"{x:5.0f}" for x in r[1]))
+        print("   front warp 8, cycles per step waiting for accumulator 0 / 1 :", " ".join(f"{x:5.0f}" for x in r[2][:2]))

@@ -215,3 +215,25 @@ def test_row_split_under_a_lagging_back_warp_pair(oracle, keyset):
         assert np.array_equal(got[idx], oracle.pbs(ct[idx], 1 << 20, keyset)), f"count {count}"
         # the un-stressed engine gives the same batch
     eng.close()
+
+
+def test_claim_protocol_build_agrees_with_the_producer_warp_build(oracle, keyset, engine):
+    """The default blind rotation has a dedicated BSK producer warp (16-warp build); RS_WS_PRODUCER=0 selects the 12-warp build
+    whose front warps claim the slabs.  Same ciphertexts from both, in every row-split mode, and both equal the oracle."""
+    import redsec_b200 as rs
+    os.environ["RS_WS_PRODUCER"] = "0"
+    try:
+        legacy = rs.Engine(0)
+    finally:
+        del os.environ["RS_WS_PRODUCER"]
+    legacy.load_eval_key(keyset.bsk, keyset.ksk)
+    rng = np.random.default_rng(77)
+    for count in (2, 149, 300, 601):          # split 4, split 2, un-split partial wave, un-split with a second wave
+        mu = rng.integers(-1500, 1500, count) * (1 << 20)
+        ct = oracle.encrypt(mu, 2.0 ** -15, keyset.lwe_key, 500 + count)
+        a = engine.download(engine.pbs(engine.upload(ct), 1 << 20))
+        b = legacy.download(legacy.pbs(legacy.upload(ct), 1 << 20))
+        assert np.array_equal(a, b), f"count {count}"
+        idx = np.unique(np.concatenate([rng.choice(count, min(count, 12), replace=False), [0, count - 1]]))
+        assert np.array_equal(a[idx], oracle.pbs(ct[idx], 1 << 20, keyset)), f"count {count}"
+    legacy.close()
