@@ -5,8 +5,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "redsec_b200", "libredsec_b200.so")
 KEYS = ["UBLKCP", "UTMALDG", "SYNCS", "USETMAXREG", "DFMA", "DADD", "DMUL", "DMMA", "F2I", "I2F", "LDS", "STS", "LDG", "STG", "ATOMG", "RED",
         "SHFL", "BAR", "MEMBAR", "UTCCP", "LDTM", "UTCBAR", "UTCHMMA", "UTCIMMA", "UTCQMMA", "UTCATOMSWS", "TCGEN"]
-WANT = [("blind_rotate_ws_kernelILi5ELi3ELi1ELb0", "blind_rotate_ws_kernel<5,3,1> (default, full waves)"),
-        ("blind_rotate_ws_kernelILi5ELi3ELi2ELb0", "blind_rotate_ws_kernel<5,3,2> (row-split, <= 2 ciphertexts per SM)"),
+WANT = [("blind_rotate_ws_kernelILi5ELi3ELi1ELb0ELb1", "blind_rotate_ws_kernel<5,3,SPLIT=1,STRESS=0,PRODUCER=1> (default, full waves; 16 warps, BSK producer warp)"),
+        ("blind_rotate_ws_kernelILi5ELi3ELi2ELb0ELb1", "blind_rotate_ws_kernel<5,3,2,0,1> (row-split, <= 2 ciphertexts per SM)"),
+        ("blind_rotate_ws_kernelILi5ELi3ELi4ELb0ELb1", "blind_rotate_ws_kernel<5,3,4,0,1> (row-split, <= 1 ciphertext per SM)"),
+        ("blind_rotate_ws_kernelILi5ELi3ELi1ELb0ELb0", "blind_rotate_ws_kernel<5,3,1,0,PRODUCER=0> (round-1 shape: 12 warps, front warps claim the slabs; RS_WS_PRODUCER=0)"),
         ("keyswitch_mma_kernel", "keyswitch_mma_kernel (default keyswitch for batches >= 2048: tcgen05.mma kind::i8 = UTCIMMA, accumulators in TMEM, LDTM epilogue)"),
         ("keyswitch_tiled_kernelILi64", "keyswitch_tiled_kernel<64> (shared-memory gather keyswitch, small batches)"),
         ("lwe_conv_kernelILb0", "lwe_conv_kernel<false>"),
