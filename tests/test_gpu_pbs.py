@@ -237,3 +237,27 @@ def test_claim_protocol_build_agrees_with_the_producer_warp_build(oracle, keyset
         idx = np.unique(np.concatenate([rng.choice(count, min(count, 12), replace=False), [0, count - 1]]))
         assert np.array_equal(a[idx], oracle.pbs(ct[idx], 1 << 20, keyset)), f"count {count}"
     legacy.close()
+
+
+def test_producer_knobs_do_not_change_ciphertexts(oracle, keyset, engine):
+    """RS_WS_GATE (every n-th wave of a long launch waits for the earlier waves: bounded spin on a counter the front warps bump) and
+    RS_WS_LOOKAHEAD (slabs the producer warp requests ahead of the slowest consumer) only move work in time."""
+    import redsec_b200 as rs
+    rng = np.random.default_rng(78)
+    count = 1300                                   # 325 CTAs = 2.2 waves: the second and third wave are gated
+    mu = rng.integers(-1500, 1500, count) * (1 << 20)
+    ct = oracle.encrypt(mu, 2.0 ** -15, keyset.lwe_key, 900)
+    want = engine.download(engine.pbs(engine.upload(ct), 1 << 20))
+    idx = np.unique(np.concatenate([rng.choice(count, 16, replace=False), [0, 591, 592, count - 1]]))
+    assert np.array_equal(want[idx], oracle.pbs(ct[idx], 1 << 20, keyset))
+    for env in ({"RS_WS_GATE": "1"}, {"RS_WS_GATE": "2", "RS_WS_LOOKAHEAD": "2"}, {"RS_WS_LOOKAHEAD": "1"}):
+        os.environ.update(env)
+        try:
+            eng = rs.Engine(0)
+        finally:
+            for k in env:
+                del os.environ[k]
+        eng.load_eval_key(keyset.bsk, keyset.ksk)
+        got = eng.download(eng.pbs(eng.upload(ct), 1 << 20))
+        eng.close()
+        assert np.array_equal(got, want), env
