@@ -547,9 +547,14 @@ public:
         RS_TRY(tree.alloc(plan->buf_count));
         RS_TRY(pooled.alloc(plan->out_count));
         const size_t S = RS_LWE_STRIDE;
-        // blocks of output rows: enough work per block to keep a launch a few waves long, a handful of blocks per lane
+        // Default: ONE launch per tree level (sign, then each OR level) -- with every launch tens of waves long the partly filled last
+        // wave costs ~1 %.  RS_POOL_BLOCKS=1 selects the block-pipelined form instead: blocks of output rows issued round-robin on two
+        // lanes so that one block's tail wave overlaps the other's launch.  Measured at the sizes one rank sees when cifar/binarynet
+        // runs on 1 / 2 / 8 GPUs it is never faster and 4 % slower on the largest 8-GPU shard (the blocks' own launches are only 1-3
+        // waves long; scripts/pool_block_ab.py, profiles/r2_pool_block_ab.log), and it is the one place where kernels of this
+        // library run concurrently, so it is off by default.
         int nb = 1;
-        if (plan->blockable && mp_out_h > 1 && !getenv("RS_NO_LANES")) {
+        if (plan->blockable && mp_out_h > 1 && getenv("RS_POOL_BLOCKS") && !getenv("RS_NO_LANES")) {
             const size_t waves = cur_count / kWaveCts;
             nb = (int)std::min<size_t>((size_t)mp_out_h, std::min<size_t>(16, waves / 3));
             if (nb < 2) nb = 1;

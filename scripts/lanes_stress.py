@@ -1,5 +1,6 @@
 """Stress: block-pipelined max-pool layer (lanes) vs the single-launch form, repeated; reports where rows differ."""
 import os, sys
+os.environ["RS_POOL_BLOCKS"] = "1"      # the block-pipelined form is opt-in since the end of round 2
 import numpy as np
 sys.path.insert(0, '.')
 import redsec_b200 as rs

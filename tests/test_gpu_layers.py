@@ -310,8 +310,8 @@ def test_full_size_layers_sampled_ciphertext_equality(oracle, keyset, engine, na
 
 
 def test_lanes_do_not_change_a_max_pool_layer(oracle, keyset, engine, tmp_path, monkeypatch):
-    """The block-pipelined max-pool layer (blocks of output rows issued round-robin on the context's lanes) produces the same
-    ciphertexts as the single-launch form (RS_NO_LANES=1) and as the oracle's OR tree on sampled outputs.  One conv layer of
+    """The block-pipelined max-pool layer (RS_POOL_BLOCKS=1: blocks of output rows issued round-robin on the context's lanes) produces
+    the same ciphertexts as the default single-launch form and as the oracle's OR tree on sampled outputs.  One conv layer of
     CIFAR conv2's shape class: 16x16 pixels x 64 channels = 16 384 sign bootstraps -> 4 096 pooled outputs."""
     from oracle import layers_oracle as LO
     nets = _nets()
@@ -324,13 +324,13 @@ def test_lanes_do_not_change_a_max_pool_layer(oracle, keyset, engine, tmp_path, 
     ct = oracle.encrypt((bits * LO.UNIT) & 0xFFFFFFFF, 2.0 ** -25, keyset.lwe_key, 47)
     net = nets.EncryptedNet(engine, spec)
     x = engine.upload(ct)
+    monkeypatch.setenv("RS_POOL_BLOCKS", "1")
     y_lanes, _, _ = net.layer_forward(0, x)
     got = engine.download(y_lanes)
     assert engine.lib.rs_lane_count(engine.ctx) >= 2, "the layer is large enough to be cut into blocks"
-    monkeypatch.setenv("RS_NO_LANES", "1")
+    monkeypatch.delenv("RS_POOL_BLOCKS")
     y_single, _, _ = net.layer_forward(0, x)
     assert np.array_equal(engine.download(y_single), got)
-    monkeypatch.delenv("RS_NO_LANES")
     L = LO.prepare(spec, spec["weights"])[0]
     idx = np.unique(np.concatenate([rng.choice(got.shape[0], 60, replace=False), [0, got.shape[0] - 1]]))
     assert np.array_equal(got[idx], LO.enc_layer_rows(L, ct, idx, keyset))
