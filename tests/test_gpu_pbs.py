@@ -261,3 +261,34 @@ def test_producer_knobs_do_not_change_ciphertexts(oracle, keyset, engine):
         got = eng.download(eng.pbs(eng.upload(ct), 1 << 20))
         eng.close()
         assert np.array_equal(got, want), env
+
+
+def test_small_last_wave_runs_row_split(oracle, keyset, engine):
+    """A multi-wave batch whose last wave holds <= 2 ciphertexts per SM is cut into an un-split launch and a row-split one
+    (api.cu launch_blind_rotate); test-vector batches only when the cut falls on a multiple of the table count.  Ciphertexts
+    equal the oracle's on both sides of the cut, and equal the single-launch result (RS_WS_TAIL_SPLIT=0)."""
+    import redsec_b200 as rs
+    os.environ["RS_WS_TAIL_SPLIT"] = "0"
+    try:
+        whole = rs.Engine(0)
+    finally:
+        del os.environ["RS_WS_TAIL_SPLIT"]
+    whole.load_eval_key(keyset.bsk, keyset.ksk)
+    rng = np.random.default_rng(79)
+    for count in (592 + 100, 2 * 592 + 280):
+        mu = rng.integers(-1500, 1500, count) * (1 << 20)
+        ct = oracle.encrypt(mu, 2.0 ** -15, keyset.lwe_key, 700 + count)
+        got = engine.download(engine.pbs(engine.upload(ct), 1 << 20))
+        assert np.array_equal(got, whole.download(whole.pbs(whole.upload(ct), 1 << 20))), count
+        head = count - count % 592
+        idx = np.unique(np.concatenate([rng.choice(count, 10, replace=False), [0, head - 1, head, head + 1, count - 1]]))
+        assert np.array_equal(got[idx], oracle.pbs(ct[idx], 1 << 20, keyset)), count
+    count = 592 + 60
+    ct = oracle.encrypt(rng.integers(-1500, 1500, count) * (1 << 20), 2.0 ** -15, keyset.lwe_key, 990)
+    for tables in (4, 3):                     # 592 % 4 == 0: cut; 592 % 3 != 0: one launch
+        luts = (rng.integers(-1000, 1000, size=(tables, 1024)) * (1 << 20) & 0xFFFFFFFF).astype(np.uint32)
+        got = engine.download(engine.pbs_lut(engine.upload(ct), luts))
+        idx = np.array([0, 1, 2, 3, 590, 591, 592, 593, 594, 595, count - 1])
+        want = np.concatenate([oracle.pbs_lut(ct[i:i + 1], luts[(i % tables):(i % tables) + 1], keyset) for i in idx])
+        assert np.array_equal(got[idx], want), tables
+    whole.close()
