@@ -55,6 +55,7 @@ struct rs_ctx {
     bool key_loaded = false;
     // tensor-core keyswitch (variant 2): pre-tiled u8 key, transposed a' scratch
     uint8_t* kskb = nullptr;
+    bool kskb_ready = false;      // false until built from the CURRENT key (rs_load_eval_key resets it)
     uint32_t* abar_t = nullptr; size_t abar_cap = 0;
     uint32_t* bprime = nullptr; size_t bprime_cap = 0;
     // scratch (grow-only; no allocation on the steady-state hot path)
@@ -314,10 +315,11 @@ int launch_keyswitch(rs_ctx* ctx, uint32_t* out, const uint32_t* ext, size_t cou
     const bool use_mma = ctx->ks_variant == 2 || (ctx->ks_variant == 0 && count >= (size_t)ctx->ks_mma_min);
     if (use_mma) {
         // exact int8 GEMM on the tensor cores (keyswitch_mma.cuh): tiled key built on first use from the padded table
-        if (!ctx->kskb) {
-            RS_CUDA(ctx, cudaMalloc(&ctx->kskb, rs::KSKB_BYTES));
+        if (!ctx->kskb) RS_CUDA(ctx, cudaMalloc(&ctx->kskb, rs::KSKB_BYTES));
+        if (!ctx->kskb_ready) {          // first use, or the first use after another rs_load_eval_key
             LaunchScope ls(ctx, RS_K_OTHER);
             rs::kskb_build_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->ksk, ctx->kskb);
+            ctx->kskb_ready = true;
         }
         const int stride = (int)((count + rs::KM_CTS - 1) / rs::KM_CTS) * rs::KM_CTS;
         if (int r = grow(ctx, &ctx->abar_t, &ctx->abar_cap, (size_t)rs::N * stride)) return r;
@@ -601,6 +603,7 @@ int rs_load_eval_key(rs_ctx* ctx, const uint32_t* bsk_host, const uint32_t* ksk_
     RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RS_CUDA(ctx, cudaFree(stage));
     ctx->key_loaded = true;
+    ctx->kskb_ready = false;      // the tensor-core keyswitch table is rebuilt from the new key on its next use
     return RS_OK;
 }
 

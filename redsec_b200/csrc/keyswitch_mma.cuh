@@ -68,7 +68,7 @@ __global__ void kskb_build_kernel(const uint32_t* __restrict__ ksk /*[N][t][8][L
                 const int pair = step * KM_PAIRS + kc * 2 + (b >> 3), d = b & 7;
                 const int i = pair / KS_T, j = pair % KS_T;
                 if (d) {
-                    const uint32_t v = ksk[(((size_t)i * KS_T + j) * KS_BASE + d) * LWE_STRIDE + word];
+                    const uint32_t v = __ldcg(ksk + (((size_t)i * KS_T + j) * KS_BASE + d) * LWE_STRIDE + word);   // written by ksk_pad_kernel, possibly twice (key reload): L2 only
                     out[b >> 2] |= ((v >> (8 * limb)) & 255u) << (8 * (b & 3));
                 }
             }

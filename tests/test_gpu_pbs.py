@@ -292,3 +292,23 @@ def test_small_last_wave_runs_row_split(oracle, keyset, engine):
         want = np.concatenate([oracle.pbs_lut(ct[i:i + 1], luts[(i % tables):(i % tables) + 1], keyset) for i in idx])
         assert np.array_equal(got[idx], want), tables
     whole.close()
+
+
+def test_second_key_load_rebuilds_every_keyswitch_table(oracle, keyset):
+    """rs_load_eval_key twice on one context: the keyswitch tables derived from the key -- the tiled table of the gather kernel and
+    the byte-limb table of the tensor-core kernel, which is built lazily on first use -- must follow the second key."""
+    import redsec_b200 as rs
+    rng = np.random.default_rng(80)
+    ksk2 = rng.integers(0, 2 ** 32, size=keyset.ksk.size, dtype=np.uint64).astype(np.uint32)     # any table is a valid keyswitch key
+    second = oracle.KeySet(keyset.lwe_key, keyset.tlwe_key, keyset.bsk, ksk2)
+    ext = rng.integers(0, 2 ** 32, size=(600, 1025), dtype=np.uint64).astype(np.uint32)
+    eng = rs.Engine(0)
+    try:
+        for ks in (keyset, second):
+            eng.load_eval_key(ks.bsk, ks.ksk)
+            want = oracle.keyswitch(ext, ks)
+            for variant in (2, 3):                 # tensor cores, shared-memory gather
+                eng.set_ks_variant(variant)
+                assert np.array_equal(eng.keyswitch(ext), want), f"variant {variant}"
+    finally:
+        eng.close()
