@@ -1,28 +1,39 @@
-// dropin/lib/GPU/BinOps_gpu.cuh -- BinOps:: with the reference's GPU prototypes (lib/GPU/BinOps_gpu.cuh:7-47); per-ciphertext
-// calls over the engine's batch API (see gates.cuh).
+// dropin/lib/GPU/BinOps_gpu.cuh -- the BinOps:: surface of the reference's GPU build (prototypes as at
+// lib/GPU/BinOps_gpu.cuh:7-47 so that lib/GPU/BinLayer.cu and the net drivers compile unchanged); bodies in
+// dropin/src/ops_shim.cpp, each a count-1 call on the engine's batch API (gates.cuh says what that costs).
 #pragma once
 #include <cstdio>
 #include "Layer.cuh"
 #include "gates.cuh"
-namespace BinOps
-{
-    void multiply(tBit* result, const tBit* a, const uint8_t b, redcufhe::Stream curr_sm);
-    void multiply_pc_ints(redcufhe::Ctxt& result, redcufhe::Ctxt& in1, const uint16_t* multicand, uint8_t in1_bits, uint8_t in2_bits, redcufhe::Stream curr_sm);
-    void add_bit(tMultiBit* result, const tBit* a, const tBit* b, redcufhe::Stream curr_sm);
-    void add(tMultiBit* result, const tMultiBit* a, const tMultiBit* b, uint8_t bits, redcufhe::Stream curr_sm);
-    void add_pc_ints(redcufhe::Ctxt& result, redcufhe::Ctxt& in1, const uint16_t* addend, uint8_t in_bits, redcufhe::Stream curr_sm);
-    void int_add(redcufhe::Ctxt& result, const redcufhe::Ctxt& a, const redcufhe::Ctxt& b, redcufhe::Stream curr_sm);
-    void inc(tMultiBit* result, const tMultiBit* a, const tBit* b, redcufhe::Stream curr_sm);
-    void max(tBit* result, const tBit* a, const tBit* b, redcufhe::Stream curr_sm);
-    void shift(tMultiBit* result, tMultiBit* in1, uint8_t input_bits, uint8_t shift_bits, redcufhe::Stream curr_sm);
-    void relu(tFixedPoint* result, tMultiBit* in1, uint8_t input_bits, redcufhe::Stream curr_sm);
-    void binarize_int(redcufhe::Ctxt& result, redcufhe::Stream curr_sm);
-    void binarize(tBit* result, const tMultiBit* a);
-    void unbinarize_int(redcufhe::Ctxt& result, redcufhe::Stream curr_sm);
-    void unbinarize_int_inv(redcufhe::Ctxt& result, redcufhe::Stream curr_sm);
-    void get_filters(FILE* fd_in, tBitPacked** p_filt_b, uint32_t len);
-    void get_bitfilters(FILE* fd_in, tBitPacked** p_filt_b, uint32_t len);
-    void get_intfilters(FILE* fd_in, tMultiBitPacked** p_filt_b, uint32_t len);
-    void get_intfilters_ptxt(FILE* fd_in, uint16_t* p_filt_mb, uint32_t len);
-    void get_ternfilters(FILE* fd_in, uint8_t* p_filt_b, uint8_t* p_tern, uint32_t len, float thresh);
-}
+
+namespace BinOps {
+using Stream = redcufhe::Stream;
+using Ctxt = redcufhe::Ctxt;
+
+// ---- weight-file readers (host only; the var_prep.dat block formats of SURVEY 5.4)
+void get_filters(FILE* weights, tBitPacked** packed_out, uint32_t count);            // float weights -> trivial +-1/8 bits
+void get_bitfilters(FILE* weights, tBitPacked** packed_out, uint32_t count);         // packed bits, MSB first
+void get_ternfilters(FILE* weights, uint8_t* sign_out, uint8_t* nonzero_out, uint32_t count, float threshold);
+void get_intfilters(FILE* weights, tMultiBitPacked** packed_out, uint32_t count);    // int32 block -> trivial samples, units of 1/4096
+void get_intfilters_ptxt(FILE* weights, uint16_t* values_out, uint32_t count);
+
+// ---- one bootstrap per call
+void binarize_int(Ctxt& io, Stream st);                   // sign, -> +-1/4096 (lib/BinOps_enc.cpp:182-186)
+void unbinarize_int(Ctxt& io, Stream st);                 // sign, -> +-1/2048 (:188-192)
+void unbinarize_int_inv(Ctxt& io, Stream st);             // the same with the sign flipped
+void max(tBit* out, const tBit* lhs, const tBit* rhs, Stream st);            // OR gate at +-1/8
+
+// ---- gate-level bit-sliced arithmetic (one bootstrap per gate)
+void add_bit(tMultiBit* sum_out, const tBit* lhs, const tBit* rhs, Stream st);                          // XOR + AND
+void add(tMultiBit* sum_out, const tMultiBit* lhs, const tMultiBit* rhs, uint8_t bits, Stream st);     // ripple carry of full adders
+void inc(tMultiBit* sum_out, const tMultiBit* value, const tBit* carry_in, Stream st);                 // XOR / AND chain
+void relu(tFixedPoint* out, tMultiBit* value, uint8_t value_bits, Stream st);                          // value_bits - 1 AND gates with the top slice
+
+// ---- bootstrap-free: one rs_lwe_axpby of count 1, or copies / negations
+void int_add(Ctxt& out, const Ctxt& lhs, const Ctxt& rhs, Stream st);
+void add_pc_ints(Ctxt& out, Ctxt& value, const uint16_t* plain_addend, uint8_t value_bits, Stream st);   // addend in units of 1/4096
+void multiply_pc_ints(Ctxt& out, Ctxt& value, const uint16_t* plain_factor, uint8_t value_bits, uint8_t factor_bits, Stream st);
+void multiply(tBit* out, const tBit* value, const uint8_t plain_bit, Stream st);      // XNOR with a plaintext bit: NOT or copy
+void binarize(tBit* sign_out, const tMultiBit* value);                               // copy of the top slice
+void shift(tMultiBit* out, tMultiBit* value, uint8_t value_bits, uint8_t by_bits, Stream st);            // arithmetic right shift of the slices
+}  // namespace BinOps

@@ -1,16 +1,24 @@
-// dropin/lib/GPU/IntOps_gpu.cuh -- IntOps:: with the reference's GPU prototypes (lib/GPU/IntOps_gpu.cuh:6-29).
+// dropin/lib/GPU/IntOps_gpu.cuh -- the IntOps:: surface the reference's GPU layer code calls (prototypes as at
+// lib/GPU/IntOps_gpu.cuh:6-29, so that callers compile unchanged), implemented in dropin/src/ops_shim.cpp as count-1 calls on the
+// engine's batch API.  Grouped by what a call costs here:
 #pragma once
 #include "Layer.cuh"
 #include "gates.cuh"
-namespace IntOps
-{
-    void add(tFixedPoint* result, const tFixedPoint* a, const tFixedPoint* b, redcufhe::Stream curr_sm);
-    void subtract(tFixedPoint* result, const tFixedPoint* a, const tFixedPoint* b, redcufhe::Stream curr_sm);
-    void binarize(tBit* result, const tFixedPoint* a, redcufhe::Stream curr_sm);
-    void binarize_int(tBit* result, redcufhe::Stream curr_sm);
-    void invert(tFixedPoint* result, const tFixedPoint* a, const uint8_t* b, redcufhe::Stream curr_sm);
-    void multiply_pc_ints(redcufhe::Ctxt& result, redcufhe::Ctxt& in1, const uint16_t* multicand, uint8_t in1_bits, uint8_t in2_bits, redcufhe::Stream curr_sm);
-    void add_pc_ints(redcufhe::Ctxt& result, redcufhe::Ctxt& in1, const uint16_t* addend, uint8_t in1_bits, redcufhe::Stream curr_sm);
-    void relu(tFixedPoint* result, tFixedPoint* in1, uint8_t input_bits, redcufhe::Stream curr_sm);
-    void shift(tFixedPoint* result, tFixedPoint* in1, uint8_t input_bits, uint8_t shift_bits, redcufhe::Stream curr_sm);
-}
+
+namespace IntOps {
+using Stream = redcufhe::Stream;
+using Ctxt = redcufhe::Ctxt;
+
+// ---- bootstraps
+void binarize_int(tBit* io, Stream st);                                          // one sign bootstrap, in place, -> +-1/4096
+void relu(tFixedPoint* out, tFixedPoint* value, uint8_t value_bits, Stream st);  // value_bits - 1 AND gates with the top slice
+
+// ---- bootstrap-free: one rs_lwe_axpby of count 1, or copies / negations of bit slices
+void add(tFixedPoint* out, const tFixedPoint* lhs, const tFixedPoint* rhs, Stream st);
+void subtract(tFixedPoint* out, const tFixedPoint* lhs, const tFixedPoint* rhs, Stream st);
+void add_pc_ints(Ctxt& out, Ctxt& value, const uint16_t* plain_addend, uint8_t value_bits, Stream st);     // addend in units of 1/4096
+void multiply_pc_ints(Ctxt& out, Ctxt& value, const uint16_t* plain_factor, uint8_t value_bits, uint8_t factor_bits, Stream st);
+void binarize(tBit* sign_out, const tFixedPoint* value, Stream st);              // copy of the top slice of a bit-sliced value
+void invert(tFixedPoint* out, const tFixedPoint* value, const uint8_t* keep, Stream st);          // *keep == 1: copy, else NOT, per slice
+void shift(tFixedPoint* out, tFixedPoint* value, uint8_t value_bits, uint8_t by_bits, Stream st); // arithmetic right shift of the slices
+}  // namespace IntOps

@@ -8,22 +8,37 @@
 #include "REDcuFHE/redcufhe_gpu.cuh"
 #include <vector>
 
-void CtxtCopyD2H(const redcufhe::Ctxt& c, redcufhe::Stream st);   // no-ops: a facade Ctxt is host memory
-void CtxtCopyH2D(const redcufhe::Ctxt& c, redcufhe::Stream st);
-void redsec_binarize_bootstrap(redcufhe::Ctxt& out, redcufhe::Stream st);
-void redsec_unbinarize_bootstrap(redcufhe::Ctxt& out, redcufhe::Stream st);
-void redsec_unbinarize_bootstrap_inv(redcufhe::Ctxt& out, redcufhe::Stream st);
-void bootsNAND(redcufhe::Ctxt& out, const redcufhe::Ctxt& in0, const redcufhe::Ctxt& in1, redcufhe::Stream st);
-void bootsOR(redcufhe::Ctxt& out, const redcufhe::Ctxt& in0, const redcufhe::Ctxt& in1, redcufhe::Stream st);
-void bootsAND(redcufhe::Ctxt& out, const redcufhe::Ctxt& in0, const redcufhe::Ctxt& in1, redcufhe::Stream st);
-void bootsNOR(redcufhe::Ctxt& out, const redcufhe::Ctxt& in0, const redcufhe::Ctxt& in1, redcufhe::Stream st);
-void bootsXOR(redcufhe::Ctxt& out, const redcufhe::Ctxt& in0, const redcufhe::Ctxt& in1, redcufhe::Stream st);
-void bootsXNOR(redcufhe::Ctxt& out, const redcufhe::Ctxt& in0, const redcufhe::Ctxt& in1, redcufhe::Stream st);
-void levelNOT(redcufhe::Ctxt& out, const redcufhe::Ctxt& in0, redcufhe::Stream st);
-void NoiselessTrivial(redcufhe::Ctxt& result, redcufhe::Torus mu);
-void levelCONSTANT(redcufhe::Ctxt& result, int32_t value);
-void add_int(redcufhe::Ctxt& sum, const redcufhe::Ctxt& a, const redcufhe::Ctxt& b, redcufhe::Stream st);
-void mul_int(redcufhe::Ctxt& prod, const redcufhe::Ctxt& a, uint16_t b);
-void sub_int(redcufhe::Ctxt& res, const redcufhe::Ctxt& a, const redcufhe::Ctxt& b, redcufhe::Stream st);
-void bootstrapped_full_adder(redcufhe::Ctxt& sum, redcufhe::Ctxt& carry_out, redcufhe::Ctxt& temp_a, redcufhe::Ctxt& temp_b,
-                             const redcufhe::Ctxt& a, const redcufhe::Ctxt& b, const redcufhe::Ctxt& carry_in, redcufhe::Stream st);
+namespace redsec_facade {
+using Ctxt = redcufhe::Ctxt;
+using Stream = redcufhe::Stream;
+}
+
+// ---- two-input gates, inputs and output at +-1/8: one rs_gate_batch of count 1 each
+#define RS_FACADE_GATE2(name) void name(redsec_facade::Ctxt& out, const redsec_facade::Ctxt& lhs, const redsec_facade::Ctxt& rhs, redsec_facade::Stream st)
+RS_FACADE_GATE2(bootsAND);
+RS_FACADE_GATE2(bootsNAND);
+RS_FACADE_GATE2(bootsOR);
+RS_FACADE_GATE2(bootsNOR);
+RS_FACADE_GATE2(bootsXOR);
+RS_FACADE_GATE2(bootsXNOR);
+#undef RS_FACADE_GATE2
+void bootstrapped_full_adder(redsec_facade::Ctxt& sum, redsec_facade::Ctxt& carry_out, redsec_facade::Ctxt& scratch_a, redsec_facade::Ctxt& scratch_b,
+                             const redsec_facade::Ctxt& lhs, const redsec_facade::Ctxt& rhs, const redsec_facade::Ctxt& carry_in,
+                             redsec_facade::Stream st);
+
+// ---- sign bootstraps, in place: one rs_pbs_batch of count 1 each
+void redsec_binarize_bootstrap(redsec_facade::Ctxt& io, redsec_facade::Stream st);           // -> +-1/4096
+void redsec_unbinarize_bootstrap(redsec_facade::Ctxt& io, redsec_facade::Stream st);         // -> +-1/2048
+void redsec_unbinarize_bootstrap_inv(redsec_facade::Ctxt& io, redsec_facade::Stream st);     // -> -+1/2048
+
+// ---- bootstrap-free: one rs_lwe_axpby of count 1 each (NoiselessTrivial / levelCONSTANT only fill the host words)
+void levelNOT(redsec_facade::Ctxt& out, const redsec_facade::Ctxt& value, redsec_facade::Stream st);
+void add_int(redsec_facade::Ctxt& out, const redsec_facade::Ctxt& lhs, const redsec_facade::Ctxt& rhs, redsec_facade::Stream st);
+void sub_int(redsec_facade::Ctxt& out, const redsec_facade::Ctxt& lhs, const redsec_facade::Ctxt& rhs, redsec_facade::Stream st);
+void mul_int(redsec_facade::Ctxt& out, const redsec_facade::Ctxt& value, uint16_t plain_factor);
+void NoiselessTrivial(redsec_facade::Ctxt& out, redcufhe::Torus mu);
+void levelCONSTANT(redsec_facade::Ctxt& out, int32_t value);
+
+// ---- no-ops here: a facade Ctxt lives in host memory, the engine moves data itself
+void CtxtCopyH2D(const redsec_facade::Ctxt& c, redsec_facade::Stream st);
+void CtxtCopyD2H(const redsec_facade::Ctxt& c, redsec_facade::Stream st);
